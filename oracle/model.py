@@ -1,0 +1,82 @@
+"""Oracle (test infrastructure): the network of models/gnn.py in plain CPU torch.
+
+Restates DeepSetEncoder (models/gnn.py:48-68; members are pooled with SUM, :67),
+ResGnn (:10-45; layer 0 `relu(conv)`, layers i>0 `x + relu(conv)`, every layer
+H->H, node MLP Linear-BatchNorm1d-ReLU-Linear :21-26) and GNN (:71-141).
+Module/parameter names are chosen so `state_dict()` has exactly the reference's
+60 keys and a checkpoint loads into the reference, this oracle
+and the CUDA-backed model alike.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import losses
+from .pyg import GINEConv
+
+
+def _mlp(n_in, n_hidden, n_out):
+    return nn.Sequential(nn.Linear(n_in, n_hidden), nn.ReLU(), nn.Linear(n_hidden, n_out))
+
+
+class DeepSetEncoder(nn.Module):
+    def __init__(self, ensemble_in_dim, hidden_channels, out_channels):
+        super().__init__()
+        self.phi = _mlp(ensemble_in_dim, hidden_channels, hidden_channels)
+        self.rho = _mlp(hidden_channels, hidden_channels, out_channels)
+
+    def forward(self, members):                 # [M, Em, F]
+        return self.rho(self.phi(members).sum(dim=1))
+
+
+class ResGnn(nn.Module):
+    def __init__(self, in_channels, out_channels, num_layers, hidden_channels):
+        super().__init__()
+        assert num_layers > 0, "num_layers must be > 0."
+        self.convolutions = nn.ModuleList()
+        for _ in range(num_layers):
+            node_mlp = nn.Sequential(nn.Linear(in_channels, hidden_channels),
+                                     nn.BatchNorm1d(hidden_channels), nn.ReLU(),
+                                     nn.Linear(hidden_channels, hidden_channels))
+            self.convolutions.append(GINEConv(nn=node_mlp, train_eps=True, edge_dim=1))
+
+    def forward(self, x, edge_index, edge_attr):
+        x, edge_attr = x.float(), edge_attr.float()
+        for i, conv in enumerate(self.convolutions):
+            h = torch.relu(conv(x, edge_index, edge_attr))
+            x = h if i == 0 else x + h
+        return x
+
+
+_HEAD_WIDTH = {"NormalCRPS": 2, "MixedNormalCRPS": 3}
+
+
+class GNN(nn.Module):
+    def __init__(self, in_channels, hidden_channels_gnn, out_channels_gnn, num_layers_gnn,
+                 optimizer_class=None, optimizer_params=None, loss="MixedLoss",
+                 grad_u=False, u=0.5, xi=0.5):
+        super().__init__()
+        self.loss, self.grad_u, self.u, self.xi = loss, grad_u, u, xi
+        if loss == "NormalCRPS":
+            self.loss_fn = losses.NormalCRPS()
+        elif loss == "MixedNormalCRPS":
+            self.loss_fn = losses.MixedNormalCRPS()
+        elif loss == "MixedLoss":
+            learn_u = grad_u == "True"                       # string compare, models/gnn.py:98
+            self.loss_fn = losses.MixedLoss(grad_u=learn_u, xi=xi, u=None if learn_u else u)
+        self.out_channels = _HEAD_WIDTH.get(loss, 5 if grad_u == "True" else 4)
+        h = hidden_channels_gnn
+        self.deepset = DeepSetEncoder(in_channels, h, h)
+        self.dim_red = nn.Linear(in_channels + h, h)
+        self.conv = ResGnn(h, h, num_layers_gnn, h)
+        self.aggr = nn.Linear(out_channels_gnn, self.out_channels)
+        self.optimizer_class, self.optimizer_params = optimizer_class, optimizer_params
+
+    def raw_head(self, data):
+        emb = self.deepset(data.ensemble)
+        node = self.dim_red(torch.cat([data.x, emb], dim=1))
+        return self.aggr(self.conv(node, data.edge_index, data.edge_attr))
+
+    def forward(self, data):
+        return losses.postprocess(self.raw_head(data), self.loss, self.grad_u)

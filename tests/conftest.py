@@ -1,0 +1,50 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_graph():
+    return np.load(os.path.join(GOLDEN, "graph.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_crps():
+    return np.load(os.path.join(GOLDEN, "crps.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_model():
+    return np.load(os.path.join(GOLDEN, "model.npz"))
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| — the tolerance definition of SURVEY.md 8c."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    ok = np.isfinite(b)          # "finite where the reference is finite" (hard parts)
+    if not ok.any():
+        return 0.0
+    assert np.isfinite(a[ok]).all(), "non-finite value where the reference is finite"
+    return float(np.abs(a[ok] - b[ok]).max() / max(np.abs(b[ok]).max(), 1e-30))
+
+
+def grad_scale(key, want_max, lookup_max):
+    """Scale for gradient comparisons.  The bias of the Linear in front of BatchNorm
+    (`...nn.0.bias`) has an exactly-zero true gradient (BN removes the mean), so the reference value
+    is rounding noise (~1e-9); it is compared on the scale of its weight's gradient instead."""
+    if key.endswith(".nn.0.bias"):
+        return max(lookup_max(key[:-4] + "weight"), 1e-12)
+    return max(want_max, 1e-12)
