@@ -1,0 +1,232 @@
+/* rc_b200.h — C ABI of the B200 (sm_100a) kernels behind raincast-gnn's training hot path.
+ *
+ * The reference (SohirMaskey/raincast-gnn) is pure Python on top of PyTorch + torch-geometric and
+ * has no FFI of its own; each entry point below names the reference code (file:line under the
+ * reference tree) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, an RC_ERR_* code otherwise; rc_last_error() gives text.
+ *   - The caller (PyTorch) owns every buffer: inputs, outputs, saved activations and workspaces.
+ *     The library never allocates, frees or synchronises, so every call is CUDA-graph capturable.
+ *   - Pointers are DEVICE pointers unless the function name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - Matrices are row-major float32 with an explicit leading dimension; index arrays are int32
+ *     on the device (the reference's int64 edge_index is narrowed once, in rc_csr_build*).
+ */
+#ifndef RC_B200_H
+#define RC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RC_OK 0
+#define RC_ERR_ARG 1       /* bad size / null pointer / unsupported shape */
+#define RC_ERR_CUDA 2      /* a CUDA runtime call failed (launch error etc.) */
+#define RC_ERR_WORKSPACE 3 /* workspace too small */
+#define RC_ERR_GRAPH 4     /* edge_index holds a node id outside [0, M) */
+
+int rc_version(void);
+const char* rc_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t rc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Station graph: construction and layout
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Radius graph from a dense distance matrix, utils/data.py:261-284 (build_edge_index_and_attr):
+ * non-self edges with D[i,j] <= max_dist in row-major order (src=i ascending, then dst=j), attr =
+ * (d / max d)^-1 in float32, then N self loops with attr 1.0.  Two calls: count, then fill. */
+int rc_radius_graph_count_host(const float* dist, int n, float max_dist, int64_t* n_edges);
+int rc_radius_graph_fill_host(const float* dist, int n, float max_dist, int64_t n_edges,
+                              int64_t* edge_index /* [2, n_edges] */, float* edge_attr /* [n_edges] */);
+
+/* Same edge order from 2-D coordinates with a cell grid (no N x N matrix), for graphs the dense
+ * function cannot hold (BASELINE.json config 4: 100k nodes).  Distances are float64 Euclidean
+ * rounded to float32, as the synthetic generator of SURVEY.md 8d defines them. */
+int rc_radius_graph_coords_count_host(const double* xy, int n, double max_dist, int64_t* n_edges);
+int rc_radius_graph_coords_fill_host(const double* xy, int n, double max_dist, int64_t n_edges,
+                                     int64_t* edge_index, float* edge_attr);
+
+/* dst-sorted CSR + src-sorted transpose + reverse-edge map of a (batched) edge list; replaces the
+ * per-step PyG collate + scatter indices (train.py:155-156 -> Batch.from_data_list; SURVEY.md
+ * Appendix B).  The sort is STABLE, so every row keeps the reference's edge order and
+ *   stack(col, row_of_slot)[:, inverse(perm)] == edge_index   bit for bit.
+ * Outputs (int32 / float32): rowptr[M+1], col[E], attr[E], perm[E]; t_rowptr[M+1], t_dst[E],
+ * t_attr[E], t_perm[E], t_slot[E]; rev[E] (slot of the reverse edge, -1 if absent). */
+typedef struct rc_csr {
+  int32_t* rowptr; int32_t* col; float* attr; int32_t* perm;
+  int32_t* t_rowptr; int32_t* t_dst; float* t_attr; int32_t* t_perm; int32_t* t_slot;
+  int32_t* rev;
+} rc_csr;
+
+int rc_csr_build_host(const int64_t* edge_index, const float* edge_attr, int64_t n_edges, int num_nodes,
+                      const rc_csr* out);
+size_t rc_csr_build_workspace(int64_t n_edges, int num_nodes);
+int rc_csr_build(const int64_t* edge_index, const float* edge_attr, int64_t n_edges, int num_nodes,
+                 const rc_csr* out, void* workspace, size_t workspace_bytes, int32_t* err_flag /* device, 1 int */,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GINE aggregation (PyG GINEConv message + 'add' aggregation + self term; call site
+ * models/gnn.py:27-29,39-44)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* h[i,:] = sum_{slot s in CSR row i} relu(x[col[s],:] + attr[s]*w_edge + b_edge) + (1+eps)*x[i,:]
+ * Sum order inside a row is slot order (= reference edge order): deterministic, no atomics. */
+int rc_gine_aggr_fwd(const float* x, const int32_t* rowptr, const int32_t* col, const float* attr,
+                     const float* w_edge /* [H] = lin.weight[:,0] */, const float* b_edge /* [H] */,
+                     const float* eps /* [1] */, float* h, int num_nodes, int hidden, void* stream);
+
+/* Transpose gather (atomic-free):
+ *   dx[j,:] = (1+eps)*g[j,:] + sum_{q in transpose row j} g[t_dst[q],:] * 1[x[j,:] + t_attr[q]*w + b > 0]
+ *             (+ addend[j,:] when addend != NULL: the residual branch of models/gnn.py:44)
+ * and per-block partial sums for d w_edge, d b_edge, d eps: partials[nblocks][3][H]. */
+int rc_gine_aggr_bwd_nblocks(int num_nodes, int hidden);
+int rc_gine_aggr_bwd(const float* g, const float* x, const int32_t* t_rowptr, const int32_t* t_dst,
+                     const float* t_attr, const float* w_edge, const float* b_edge, const float* eps,
+                     const float* addend, float* dx, float* partials, int num_nodes, int hidden, void* stream);
+/* d_w[H], d_b[H], d_eps[1] from the partials (fixed summation order). */
+int rc_gine_aggr_bwd_finalize(const float* partials, int nblocks, int hidden, float* d_w, float* d_b,
+                              float* d_eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense layers: one fp32 SIMT GEMM family with fused prologues / epilogues (torch.nn.Linear,
+ * BatchNorm1d and ReLU of models/gnn.py:21-26,51-62,113,123 and their backward)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* operand layouts: how the stored matrix relates to D[i,j] = sum_r A(i,r) * B(r,j) */
+#define RC_A_ROW 0 /* A stored [i][r]  (activations in forward / backward-data)            */
+#define RC_A_RED 1 /* A stored [r][i]  (grad_out in the weight-gradient GEMM, r = sample)   */
+#define RC_B_COL 0 /* B stored [j][r]  (nn.Linear weight [out,in] in forward)                */
+#define RC_B_RED 1 /* B stored [r][j]  (weight in backward-data; activations in weight-grad) */
+
+/* operand prologues, applied to stored element (row, col) while a tile is loaded */
+#define RC_OP_NONE 0
+#define RC_OP_BN_RELU 1 /* v = relu((v - p0[col]) * p1[col] * p2[col] + p3[col])   (mean, rstd, gamma, beta) */
+#define RC_OP_BITMASK 2 /* v = bit(bits[row*ld_bits + col/32], col%32) ? v : 0                                */
+#define RC_OP_AFFINE2 3 /* v = p0[col]*v + p1[col]*(aux[row*ld_aux + col] - p3[col]) + p2[col]  (BN backward) */
+
+/* epilogues on D element (i, j), after `+ bias_scale*bias[j]` */
+#define RC_EPI_NONE 0
+#define RC_EPI_RELU 1       /* D = relu(v)                                                                    */
+#define RC_EPI_RELU_RES 2   /* D = res[i,j] + relu(v); bits (optional) record v > 0        (models/gnn.py:44) */
+#define RC_EPI_BN_STATS 3   /* D = v; per row-tile column mean / M2 -> stats[tile][2][N]  (BatchNorm forward) */
+#define RC_EPI_MASK_POS 4   /* D = aux[i,j] > 0 ? v : 0                                     (ReLU backward)    */
+#define RC_EPI_BN_RELU_BWD 5 /* z = p2*(aux-p0)*p1 + p3; D = z > 0 ? v : 0; column partial sums of D and
+                               D*(aux-p0)*p1 -> stats[tile][2][N]               (ReLU + BatchNorm backward)   */
+
+typedef struct rc_operand {
+  const float* ptr; int ld;
+  int op;                     /* RC_OP_* */
+  const float* p0; const float* p1; const float* p2; const float* p3;   /* per stored column */
+  const float* aux; int ld_aux;
+  const uint32_t* bits; int ld_bits;
+} rc_operand;
+
+typedef struct rc_gemm {
+  int m, n, k;                /* D is m x n, reduction length k (first segment) */
+  int a_layout, b_layout;
+  rc_operand a, b;
+  /* optional second segment accumulated into the same D (dim_red on cat([x, emb]) without the cat,
+   * models/gnn.py:134-135); same layouts, reduction length k2, no prologues */
+  const float* a2; int lda2; const float* b2; int ldb2; int k2;
+  float* d; int ldd;
+  const float* bias; float bias_scale;
+  int epi;                    /* RC_EPI_* */
+  const float* res; int ld_res;           /* RC_EPI_RELU_RES */
+  uint32_t* bits_out; int ld_bits_out;    /* RC_EPI_RELU / RC_EPI_RELU_RES (optional) */
+  const float* e_aux; int ld_e_aux;       /* RC_EPI_MASK_POS, RC_EPI_BN_RELU_BWD */
+  const float* e_p0; const float* e_p1; const float* e_p2; const float* e_p3;
+  float* stats;                           /* RC_EPI_BN_STATS / RC_EPI_BN_RELU_BWD: [row_tiles][2][n] */
+  /* split of the reduction over gridDim.z (weight-gradient GEMMs): slice z writes its partial tile to
+   * d + z*split_stride, and (colsum_a != NULL, A stored [r][i]) the column sums of A over its slice to
+   * colsum_a + z*m  (the bias gradient).  splits <= 1: no split. */
+  int splits; long long split_stride;
+  float* colsum_a;
+  int rows_per_warp;          /* 0 = choose; else 1, 2, 4 or 8 (row tile = 8 * rows_per_warp) */
+} rc_gemm;
+
+int rc_gemm_row_tile(const rc_gemm* g);  /* the row tile the launch would use (for stats sizing)   */
+int rc_gemm_run(const rc_gemm* g, void* stream);
+
+/* BatchNorm1d training-mode statistics from the RC_EPI_BN_STATS tiles (Chan's parallel update in
+ * float64): mean[N], rstd[N] = 1/sqrt(var_biased + eps); running_mean/var updated with `momentum`
+ * and the UNBIASED variance, num_batches_tracked += 1 (torch.nn.BatchNorm1d, models/gnn.py:23). */
+int rc_bn_stats_finalize(const float* stats, int row_tiles, int row_tile, int m, int n, float eps,
+                         float momentum, float* mean, float* rstd, float* running_mean, float* running_var,
+                         int64_t* num_batches_tracked, void* stream);
+/* Eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps). */
+int rc_bn_eval_prepare(const float* running_mean, const float* running_var, int n, float eps, float* mean,
+                       float* rstd, void* stream);
+/* BatchNorm backward coefficients from the RC_EPI_BN_RELU_BWD tiles: d_gamma[N], d_beta[N] and the
+ * per-column coefficients such that d t = c0*dz + c1*(t - mean) + c2 (the RC_OP_AFFINE2 prologue with
+ * p3 = mean). */
+int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int n, const float* gamma, const float* mean,
+                       const float* rstd, float* d_gamma, float* d_beta, float* c0, float* c1, float* c2,
+                       void* stream);
+
+/* out[j] = scale * sum_{p < parts} src[p*stride + j]  (fixed order, float64 accumulator) for a
+ * table of segments; one launch finishes every split weight/bias gradient of a backward pass. */
+typedef struct rc_reduce_seg {
+  const float* src; float* dst; long long stride; int parts; int n; float scale; int accumulate;
+} rc_reduce_seg;
+int rc_reduce_segments(const rc_reduce_seg* segs_device, int n_segs, int max_n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DeepSets member MLP + pooling (models/gnn.py:48-68)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* pooled[i,:] = sum_{e < members} relu(ens[i,e,:] @ w1^T + b1)      ens [M, members, F], w1 [H, F]
+ * (the second phi Linear is applied AFTER the sum by rc_gemm_run with bias_scale = members: the sum
+ *  over members commutes with it exactly in real arithmetic). */
+int rc_deepsets_pool_fwd(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
+                         int members, int feats, int hidden, void* stream);
+/* d w1 / d b1 partials from d pooled (ReLU mask recomputed, nothing saved in forward):
+ * partials[nblocks][H*F + H]. */
+int rc_deepsets_pool_bwd_nblocks(int num_nodes, int hidden);
+int rc_deepsets_pool_bwd(const float* ens, const float* w1, const float* b1, const float* d_pooled,
+                         float* partials, int num_nodes, int members, int feats, int hidden, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Output links + closed-form CRPS (models/model_utils.py:70-113, models/loss.py:6-68,71-272,335-369)
+ * ---------------------------------------------------------------------------------------------- */
+#define RC_LOSS_NORMAL 0        /* NormalCRPS,      2 columns: mu, sigma                   */
+#define RC_LOSS_MIXED_NORMAL 1  /* MixedNormalCRPS, 3 columns: mu, sigma, p                */
+#define RC_LOSS_MIXED 2         /* MixedLoss, fixed u, 4 columns: mu, sigma, p, sigma_u    */
+#define RC_LOSS_MIXED_U 3       /* MixedLoss, learned u, 5 columns: ..., u                 */
+
+/* PostProcess forward / backward (softplus+1e-6, sigmoid, 2.12*sigmoid). */
+int rc_postprocess_fwd(const float* raw, float* post, int num_nodes, int kind, void* stream);
+int rc_postprocess_bwd(const float* raw, const float* d_post, float* d_raw, int num_nodes, int kind, void* stream);
+
+/* Per-node CRPS and its gradient in one pass.  `pred` holds post-processed parameters
+ * (raw_input = 0, the public `crps(prediction, y)` signature) or raw head outputs (raw_input = 1: the
+ * links are applied inside and d_pred is the gradient w.r.t. the raw outputs).  NaN targets are
+ * skipped (models/loss.py:216,237-241).  The kernel writes per-block partial sums; finalize produces
+ * loss_out[0] = mean over valid nodes (float64, like the reference's promoted result) and
+ * n_valid[0]; d_pred is already divided by the number of valid nodes.
+ * workspace: rc_crps_workspace(num_nodes) bytes.  xi must not be 1 or 2 (models/loss.py:121-124). */
+size_t rc_crps_workspace(int num_nodes);
+int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred /* nullable */, double* loss_out,
+                    int32_t* n_valid, int num_nodes, int kind, int raw_input, float u_fixed, float xi, float t,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser (train.py:66-69,185: torch.optim.AdamW defaults) on flat parameter / gradient buffers
+ * ---------------------------------------------------------------------------------------------- */
+/* p -= lr*wd*p; m,v update; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps); grad is first
+ * multiplied by grad_scale (1/world_size after an all-reduce SUM).  `step` is a device int64 that is
+ * incremented by the kernel, so the call is replayable inside a CUDA graph. */
+int rc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                  long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RC_B200_H */
