@@ -166,7 +166,7 @@ int rc_bn_eval_prepare(const float* running_mean, const float* running_var, int 
 /* BatchNorm backward coefficients from the RC_EPI_BN_RELU_BWD tiles: d_gamma[N], d_beta[N] and the
  * per-column coefficients such that d t = c0*dz + c1*(t - mean) + c2 (the RC_OP_AFFINE2 prologue with
  * p3 = mean). */
-int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int n, const float* gamma, const float* mean,
+int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int n, int batch_stats, const float* gamma, const float* mean,
                        const float* rstd, float* d_gamma, float* d_beta, float* c0, float* c1, float* c2,
                        void* stream);
 
@@ -174,8 +174,12 @@ int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int n, const fl
  * table of segments; one launch finishes every split weight/bias gradient of a backward pass. */
 typedef struct rc_reduce_seg {
   const float* src; float* dst; long long stride; int parts; int n; float scale; int accumulate;
+  int row_len; int dst_ld;   /* row_len > 0: element j lands at dst[(j / row_len) * dst_ld + j % row_len] */
 } rc_reduce_seg;
-int rc_reduce_segments(const rc_reduce_seg* segs_device, int n_segs, int max_n, void* stream);
+/* `segs` is a HOST array; up to RC_REDUCE_MAX_SEGS descriptors travel as kernel arguments per launch
+ * (no device-side table, so the call is graph-capturable without a staging copy). */
+#define RC_REDUCE_MAX_SEGS 16
+int rc_reduce_segments(const rc_reduce_seg* segs, int n_segs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DeepSets member MLP + pooling (models/gnn.py:48-68)

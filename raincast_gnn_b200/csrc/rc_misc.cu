@@ -56,7 +56,7 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ running_mean, c
 
 // ---------------------------------------------------------------------------- BatchNorm backward coefficients
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ stats, int row_tiles, int m, int n, const float* __restrict__ gamma,
+bn_bwd_finalize_kernel(const float* __restrict__ stats, int row_tiles, int m, int n, int batch_stats, const float* __restrict__ gamma,
                        const float* __restrict__ mean, const float* __restrict__ rstd, float* d_gamma, float* d_beta,
                        float* c0, float* c1, float* c2) {
   __shared__ double sh[8][2][33];
@@ -78,20 +78,23 @@ bn_bwd_finalize_kernel(const float* __restrict__ stats, int row_tiles, int m, in
     // d t = gamma*rstd * (dz - d_beta/M - xhat * d_gamma/M),  xhat = (t - mean) * rstd
     const double gr = (double)gamma[col] * (double)rstd[col];
     c0[col] = (float)gr;
-    c1[col] = (float)(-gr * (double)rstd[col] * dg / (double)m);
-    c2[col] = (float)(-gr * db / (double)m);
+    // (eval mode, running statistics: the mean/variance are constants and only c0 survives)
+    c1[col] = batch_stats ? (float)(-gr * (double)rstd[col] * dg / (double)m) : 0.f;
+    c2[col] = batch_stats ? (float)(-gr * db / (double)m) : 0.f;
     (void)mean;
   }
 }
 
 // ---------------------------------------------------------------------------- segmented partial reduction
-__global__ void __launch_bounds__(256) reduce_segments_kernel(const rc_reduce_seg* __restrict__ segs) {
-  const rc_reduce_seg sg = segs[blockIdx.y];
+struct ReduceArgs { rc_reduce_seg seg[RC_REDUCE_MAX_SEGS]; };
+__global__ void __launch_bounds__(256) reduce_segments_kernel(const ReduceArgs args) {
+  const rc_reduce_seg& sg = args.seg[blockIdx.y];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < sg.n; j += gridDim.x * blockDim.x) {
     double s = 0.0;
     for (int p = 0; p < sg.parts; ++p) s += (double)__ldg(sg.src + (size_t)p * sg.stride + j);
     const float v = sg.scale * (float)s;
-    sg.dst[j] = sg.accumulate ? sg.dst[j] + v : v;
+    float* out = sg.dst + (sg.row_len > 0 ? (size_t)(j / sg.row_len) * sg.dst_ld + (j % sg.row_len) : (size_t)j);
+    *out = sg.accumulate ? *out + v : v;
   }
 }
 
@@ -146,23 +149,36 @@ extern "C" int rc_bn_eval_prepare(const float* running_mean, const float* runnin
   return check_launch("bn_eval_prepare_kernel");
 }
 
-extern "C" int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int n, const float* gamma, const float* mean,
+extern "C" int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int n, int batch_stats, const float* gamma, const float* mean,
                                   const float* rstd, float* d_gamma, float* d_beta, float* c0, float* c1, float* c2,
                                   void* stream) {
   if (!stats || !gamma || !mean || !rstd || !d_gamma || !d_beta || !c0 || !c1 || !c2 || row_tiles <= 0 || m <= 0 || n <= 0)
     return fail(RC_ERR_ARG, "rc_bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<ceil_div(n, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, row_tiles, m, n, gamma, mean, rstd,
+  bn_bwd_finalize_kernel<<<ceil_div(n, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, row_tiles, m, n, batch_stats, gamma, mean, rstd,
                                                                                         d_gamma, d_beta, c0, c1, c2);
   return check_launch("bn_bwd_finalize_kernel");
 }
 
-extern "C" int rc_reduce_segments(const rc_reduce_seg* segs_device, int n_segs, int max_n, void* stream) {
-  if (!segs_device || n_segs < 0 || max_n < 0) return fail(RC_ERR_ARG, "rc_reduce_segments: bad argument");
-  if (n_segs == 0 || max_n == 0) return RC_OK;
-  int gx = ceil_div(max_n, 256);
-  if (gx > 64) gx = 64;
-  reduce_segments_kernel<<<dim3(gx, n_segs), 256, 0, static_cast<cudaStream_t>(stream)>>>(segs_device);
-  return check_launch("reduce_segments_kernel");
+extern "C" int rc_reduce_segments(const rc_reduce_seg* segs, int n_segs, void* stream) {
+  if ((!segs && n_segs > 0) || n_segs < 0) return fail(RC_ERR_ARG, "rc_reduce_segments: bad argument");
+  for (int base = 0; base < n_segs; base += RC_REDUCE_MAX_SEGS) {
+    const int cnt = n_segs - base < RC_REDUCE_MAX_SEGS ? n_segs - base : RC_REDUCE_MAX_SEGS;
+    ReduceArgs args;
+    int max_n = 0;
+    for (int i = 0; i < cnt; ++i) {
+      args.seg[i] = segs[base + i];
+      if (!args.seg[i].src || !args.seg[i].dst || args.seg[i].n < 0 || args.seg[i].parts < 0)
+        return fail(RC_ERR_ARG, "rc_reduce_segments: bad segment %d", base + i);
+      if (args.seg[i].n > max_n) max_n = args.seg[i].n;
+    }
+    for (int i = cnt; i < RC_REDUCE_MAX_SEGS; ++i) args.seg[i] = rc_reduce_seg{nullptr, nullptr, 0, 0, 0, 0.f, 0, 0, 0};
+    if (max_n == 0) continue;
+    int gx = ceil_div(max_n, 256);
+    if (gx > 64) gx = 64;
+    reduce_segments_kernel<<<dim3(gx, cnt), 256, 0, static_cast<cudaStream_t>(stream)>>>(args);
+    if (int e = check_launch("reduce_segments_kernel")) return e;
+  }
+  return RC_OK;
 }
 
 extern "C" int rc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t* step, long long n,

@@ -1,0 +1,325 @@
+"""Block-level forward / backward schedules over the C ABI (no autograd here).
+
+Every function takes plain CUDA tensors, allocates its outputs / saved activations with torch (the
+library never allocates) and issues librc_b200.so calls on the current CUDA stream, so a whole
+training step built from these blocks can be captured in one CUDA graph.  The autograd Functions in
+functional.py and the graphed engine in engine.py are both thin callers of this file.
+
+Reference arithmetic: models/gnn.py:10-141 (DeepSetEncoder, ResGnn, GNN), PyG GINEConv,
+torch.nn.BatchNorm1d / Linear; see include/rc_b200.h for the per-kernel citations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (RC_A_RED, RC_A_ROW, RC_B_COL, RC_B_RED, RC_EPI_BN_RELU_BWD, RC_EPI_BN_STATS, RC_EPI_MASK_POS,
+                   RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_OP_AFFINE2, RC_OP_BITMASK, RC_OP_BN_RELU, RC_OP_NONE)
+
+BN_EPS = 1e-5          # torch.nn.BatchNorm1d defaults (models/gnn.py:23)
+BN_MOMENTUM = 0.1
+_SM = 148
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def operand(t, ld, op=RC_OP_NONE, p=(None, None, None, None), aux=None, ld_aux=0, bits=None, ld_bits=0):
+    return _lib.rc_operand(_lib.ptr(t), ld, op, _lib.ptr(p[0]), _lib.ptr(p[1]), _lib.ptr(p[2]), _lib.ptr(p[3]),
+                           _lib.ptr(aux), ld_aux, _lib.ptr(bits), ld_bits)
+
+
+def gemm(m, n, k, a: _lib.rc_operand, b: _lib.rc_operand, d, ldd, *, a_layout=RC_A_ROW, b_layout=RC_B_COL, bias=None,
+         bias_scale=1.0, epi=RC_EPI_NONE, res=None, ld_res=0, bits_out=None, ld_bits_out=0, e_aux=None, ld_e_aux=0,
+         e_p=(None, None, None, None), stats=None, splits=1, split_stride=0, colsum_a=None, a2=None, lda2=0, b2=None,
+         ldb2=0, k2=0, rows_per_warp=0, run=True):
+    g = _lib.rc_gemm(m, n, k, a_layout, b_layout, a, b, _lib.ptr(a2), lda2, _lib.ptr(b2), ldb2, k2, _lib.ptr(d), ldd,
+                     _lib.ptr(bias), bias_scale, epi, _lib.ptr(res), ld_res, _lib.ptr(bits_out), ld_bits_out,
+                     _lib.ptr(e_aux), ld_e_aux, _lib.ptr(e_p[0]), _lib.ptr(e_p[1]), _lib.ptr(e_p[2]), _lib.ptr(e_p[3]),
+                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp)
+    if run:
+        _lib.check(_lib.lib().rc_gemm_run(C.byref(g), _stream(d)), "rc_gemm_run")
+    return g
+
+
+def gemm_row_tile(m, n, splits=1) -> int:
+    g = _lib.rc_gemm()
+    g.m, g.n, g.splits = m, n, splits
+    return int(_lib.lib().rc_gemm_row_tile(C.byref(g)))
+
+
+# --------------------------------------------------------------------------------------------- Linear
+def linear_fwd(x, w, b, *, relu=False, bias_scale=1.0):
+    """y = [relu](x @ w^T + bias_scale*b);  x [M,K], w [N,K]."""
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    gemm(m, n, k, operand(x, k), operand(w, k), y, n, bias=b, bias_scale=bias_scale,
+         epi=RC_EPI_RELU if relu else RC_EPI_NONE)
+    return y
+
+
+def linear_bwd_data(dy, w, *, mask_pos=None, w_ld=None, w_col0=0, k=None):
+    """dx = dy @ w[:, w_col0:w_col0+k]  (optionally masked by mask_pos > 0: ReLU backward).  dy [M,N], w [N,Kw]."""
+    m, n = dy.shape
+    w_ld = w.shape[1] if w_ld is None else w_ld
+    k = w.shape[1] - w_col0 if k is None else k
+    dx = torch.empty((m, k), dtype=torch.float32, device=dy.device)
+    wv = w if w_col0 == 0 else w.reshape(-1)[w_col0:]
+    gemm(m, k, n, operand(dy, n), operand(wv, w_ld), dx, k, b_layout=RC_B_RED,
+         epi=RC_EPI_MASK_POS if mask_pos is not None else RC_EPI_NONE, e_aux=mask_pos, ld_e_aux=k)
+    return dx
+
+
+def choose_splits(red_len: int, out_rows: int, out_cols: int) -> int:
+    """Reduction splits for a weight-gradient GEMM: enough CTAs to fill the SMs, >= 2 slices of 32 each."""
+    tiles = max(1, math.ceil(red_len / 32))
+    out_tiles = math.ceil(out_rows / 64) * math.ceil(out_cols / 128)
+    want = max(1, math.ceil(2 * _SM / out_tiles))
+    return int(max(1, min(want, tiles // 2 if tiles >= 2 else 1)))
+
+
+class GradSink:
+    """Collects the split partials of one backward block and finishes them with one rc_reduce_segments launch."""
+
+    def __init__(self, device):
+        self.device = device
+        self.segs = []
+        self.keep = []
+
+    def add(self, src, dst, stride, parts, n, scale=1.0, accumulate=False, row_len=0, dst_ld=0):
+        self.segs.append(_lib.rc_reduce_seg(src.data_ptr(), dst.data_ptr(), stride, parts, n, scale, int(accumulate),
+                                            row_len, dst_ld))
+        self.keep.append((src, dst))
+
+    def flush(self):
+        if self.segs:
+            arr = (_lib.rc_reduce_seg * len(self.segs))(*self.segs)
+            _lib.check(_lib.lib().rc_reduce_segments(arr, len(self.segs), torch.cuda.current_stream(self.device).cuda_stream),
+                       "rc_reduce_segments")
+        self.segs, self.keep = [], []
+
+
+def linear_bwd_weight(dy_op: _lib.rc_operand, x_op: _lib.rc_operand, m, n, k, dw, db, sink: GradSink, *, dw_ld=None,
+                      bias_scale=1.0, x2=None, dw2=None):
+    """dw[N, k] = dy^T @ x (+ db[N] = bias_scale * column sums of dy).  dy stored [M,N], x stored [M,k].
+    `dw` may be a column block of a wider matrix (dw_ld = its row stride)."""
+    dev = dw.device
+    splits = choose_splits(m, n, k)
+    dw_ld = k if dw_ld is None else dw_ld
+    direct = splits == 1 and dw_ld == k and bias_scale == 1.0
+    if direct:
+        gemm(n, k, m, dy_op, x_op, dw, k, a_layout=RC_A_RED, b_layout=RC_B_RED, colsum_a=db)
+        return
+    part = torch.empty((splits, n, k), dtype=torch.float32, device=dev)
+    cs = torch.empty((splits, n), dtype=torch.float32, device=dev) if db is not None else None
+    gemm(n, k, m, dy_op, x_op, part, k, a_layout=RC_A_RED, b_layout=RC_B_RED, splits=splits, split_stride=n * k,
+         colsum_a=cs)
+    if dw_ld == k:
+        sink.add(part, dw, n * k, splits, n * k)
+    else:                                           # column block of a wider weight matrix
+        sink.add(part, dw, n * k, splits, n * k, row_len=k, dst_ld=dw_ld)
+    if db is not None:
+        sink.add(cs, db, n, splits, n, scale=bias_scale)
+
+
+# --------------------------------------------------------------------------------------------- DeepSets
+def deepsets_fwd(P, ens):
+    """rho(sum_e phi(ens[:, e])) with the second phi Linear hoisted behind the sum (models/gnn.py:64-68)."""
+    m, em, f = ens.shape
+    h = P["phi0_w"].shape[0]
+    L = _lib.lib()
+    pooled = torch.empty((m, h), dtype=torch.float32, device=ens.device)
+    _lib.check(L.rc_deepsets_pool_fwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), pooled.data_ptr(),
+                                      m, em, f, h, _stream(ens)), "rc_deepsets_pool_fwd")
+    s2 = linear_fwd(pooled, P["phi2_w"], P["phi2_b"], bias_scale=float(em))       # sum_e (h_e W^T + b)
+    r1 = linear_fwd(s2, P["rho0_w"], P["rho0_b"], relu=True)
+    emb = linear_fwd(r1, P["rho2_w"], P["rho2_b"])
+    return emb, (ens, pooled, s2, r1)
+
+
+def deepsets_bwd(P, saved, d_emb, G):
+    ens, pooled, s2, r1 = saved
+    m, em, f = ens.shape
+    h = P["phi0_w"].shape[0]
+    L = _lib.lib()
+    dev = ens.device
+    sink = GradSink(dev)
+    ho = P["rho2_w"].shape[0]
+    # rho[2]
+    linear_bwd_weight(operand(d_emb, ho), operand(r1, h), m, ho, h, G["rho2_w"], G["rho2_b"], sink)
+    d_r1 = linear_bwd_data(d_emb, P["rho2_w"], mask_pos=r1)
+    # rho[0]
+    linear_bwd_weight(operand(d_r1, h), operand(s2, h), m, h, h, G["rho0_w"], G["rho0_b"], sink)
+    d_s2 = linear_bwd_data(d_r1, P["rho0_w"])
+    # phi[2] (after the pool): bias gradient carries the member count
+    linear_bwd_weight(operand(d_s2, h), operand(pooled, h), m, h, h, G["phi2_w"], G["phi2_b"], sink, bias_scale=float(em))
+    d_pooled = linear_bwd_data(d_s2, P["phi2_w"])
+    # phi[0] + ReLU, per member
+    nb = int(L.rc_deepsets_pool_bwd_nblocks(m, h))
+    part = torch.empty((nb, h * f + h), dtype=torch.float32, device=dev)
+    _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), d_pooled.data_ptr(),
+                                      part.data_ptr(), m, em, f, h, _stream(ens)), "rc_deepsets_pool_bwd")
+    sink.add(part, G["phi0_w"], h * f + h, nb, h * f)
+    sink.add(part.reshape(-1)[h * f:], G["phi0_b"], h * f + h, nb, h)
+    sink.flush()
+
+
+# --------------------------------------------------------------------------------------------- dim_red
+def dimred_fwd(P, x, emb):
+    """Linear(cat([x, emb])) without materialising the cat: two reduction segments (models/gnn.py:134-135)."""
+    m, f = x.shape
+    h_in = emb.shape[1]
+    w = P["dimred_w"]
+    n, ldw = w.shape
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    gemm(m, n, f, operand(x, f), operand(w, ldw), y, n, bias=P["dimred_b"],
+         a2=emb, lda2=h_in, b2=w.reshape(-1)[f:], ldb2=ldw, k2=h_in)
+    return y, (x, emb)
+
+
+def dimred_bwd(P, saved, dy, G):
+    x, emb = saved
+    m, f = x.shape
+    h_in = emb.shape[1]
+    w = P["dimred_w"]
+    n, ldw = w.shape
+    sink = GradSink(x.device)
+    dw = G["dimred_w"]
+    linear_bwd_weight(operand(dy, n), operand(x, f), m, n, f, dw[:, :f], G["dimred_b"], sink, dw_ld=ldw)
+    linear_bwd_weight(operand(dy, n), operand(emb, h_in), m, n, h_in, dw[:, f:], None, sink, dw_ld=ldw)
+    sink.flush()
+    return linear_bwd_data(dy, w, w_ld=ldw, w_col0=f, k=h_in)
+
+
+# --------------------------------------------------------------------------------------------- GINE layer
+def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
+    """One ResGnn layer (models/gnn.py:39-44): y = relu(conv(x)) for the first layer, x + relu(conv(x)) after;
+    conv = GINEConv(nn = Linear - BatchNorm1d - ReLU - Linear)."""
+    L = _lib.lib()
+    m, h = x.shape
+    dev = x.device
+    st = _stream(x)
+    agg = torch.empty_like(x)
+    _lib.check(L.rc_gine_aggr_fwd(x.data_ptr(), graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.attr.data_ptr(),
+                                  P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(), agg.data_ptr(),
+                                  m, h, st), "rc_gine_aggr_fwd")
+    hid = P["nn0_w"].shape[0]
+    t = torch.empty((m, hid), dtype=torch.float32, device=dev)
+    mean = torch.empty(hid, dtype=torch.float32, device=dev)
+    rstd = torch.empty(hid, dtype=torch.float32, device=dev)
+    if training:
+        if m < 2:
+            raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d)")
+        row_tile = gemm_row_tile(m, hid)
+        tiles = math.ceil(m / row_tile)
+        stats = torch.empty((tiles, 2, hid), dtype=torch.float32, device=dev)
+        gemm(m, hid, h, operand(agg, h), operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"], epi=RC_EPI_BN_STATS, stats=stats)
+        _lib.check(L.rc_bn_stats_finalize(stats.data_ptr(), tiles, row_tile, m, hid, BN_EPS, BN_MOMENTUM, mean.data_ptr(),
+                                          rstd.data_ptr(), P["bn_rm"].data_ptr(), P["bn_rv"].data_ptr(),
+                                          P["bn_nbt"].data_ptr(), st), "rc_bn_stats_finalize")
+    else:
+        gemm(m, hid, h, operand(agg, h), operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"])
+        _lib.check(L.rc_bn_eval_prepare(P["bn_rm"].data_ptr(), P["bn_rv"].data_ptr(), hid, BN_EPS, mean.data_ptr(),
+                                        rstd.data_ptr(), st), "rc_bn_eval_prepare")
+    out_dim = P["nn3_w"].shape[0]
+    y = torch.empty((m, out_dim), dtype=torch.float32, device=dev)
+    words = math.ceil(out_dim / 32)
+    bits = torch.empty((m, words), dtype=torch.int32, device=dev)
+    gemm(m, out_dim, hid, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), operand(P["nn3_w"], hid),
+         y, out_dim, bias=P["nn3_b"], epi=RC_EPI_RELU if first else RC_EPI_RELU_RES, res=None if first else x,
+         ld_res=h, bits_out=bits, ld_bits_out=words)
+    return y, (x, agg, t, mean, rstd, bits)
+
+
+def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True, need_dx: bool = True):
+    x, agg, t, mean, rstd, bits = saved
+    L = _lib.lib()
+    m, h = x.shape
+    hid = P["nn0_w"].shape[0]
+    out_dim = P["nn3_w"].shape[0]
+    words = bits.shape[1]
+    dev = x.device
+    st = _stream(x)
+    sink = GradSink(dev)
+    do_op = operand(dy, out_dim, RC_OP_BITMASK, bits=bits, ld_bits=words)           # d o = dy * 1[o > 0]
+    # Linear2: d W2 = d o^T u,  u = relu(BN(t)) recomputed in the prologue
+    linear_bwd_weight(do_op, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), m, out_dim, hid,
+                      G["nn3_w"], G["nn3_b"], sink)
+    # d z = (d o @ W2) * 1[BN(t) > 0], with the two BatchNorm column reductions in the epilogue
+    row_tile = gemm_row_tile(m, hid)
+    tiles = math.ceil(m / row_tile)
+    stats = torch.empty((tiles, 2, hid), dtype=torch.float32, device=dev)
+    dz = torch.empty((m, hid), dtype=torch.float32, device=dev)
+    gemm(m, hid, out_dim, do_op, operand(P["nn3_w"], hid), dz, hid, b_layout=RC_B_RED, epi=RC_EPI_BN_RELU_BWD, e_aux=t,
+         ld_e_aux=hid, e_p=(mean, rstd, P["bn_w"], P["bn_b"]), stats=stats)
+    c0 = torch.empty(hid, dtype=torch.float32, device=dev)
+    c1 = torch.empty_like(c0)
+    c2 = torch.empty_like(c0)
+    _lib.check(L.rc_bn_bwd_finalize(stats.data_ptr(), tiles, m, hid, int(training), P["bn_w"].data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    G["bn_w"].data_ptr(), G["bn_b"].data_ptr(), c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), st),
+               "rc_bn_bwd_finalize")
+    dt_op = operand(dz, hid, RC_OP_AFFINE2, (c0, c1, c2, mean), aux=t, ld_aux=hid)  # d t = c0*dz + c1*(t-mean) + c2
+    linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
+    sink.flush()
+    d_agg = torch.empty((m, h), dtype=torch.float32, device=dev)
+    gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
+    # aggregation backward (+ residual branch of layers > 0)
+    nb = int(L.rc_gine_aggr_bwd_nblocks(m, h))
+    part = torch.empty((nb, 3, h), dtype=torch.float32, device=dev)
+    dx = torch.empty((m, h), dtype=torch.float32, device=dev)
+    _lib.check(L.rc_gine_aggr_bwd(d_agg.data_ptr(), x.data_ptr(), graph.t_rowptr.data_ptr(), graph.t_dst.data_ptr(),
+                                  graph.t_attr.data_ptr(), P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(),
+                                  None if first else dy.data_ptr(), dx.data_ptr(), part.data_ptr(), m, h, st), "rc_gine_aggr_bwd")
+    _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, G["lin_w"].data_ptr(), G["lin_b"].data_ptr(),
+                                           G["eps"].data_ptr(), st), "rc_gine_aggr_bwd_finalize")
+    return dx if need_dx else None
+
+
+# --------------------------------------------------------------------------------------------- head
+def head_fwd(P, x):
+    return linear_fwd(x, P["aggr_w"], P["aggr_b"]), (x,)
+
+
+def head_bwd(P, saved, d_raw, G):
+    (x,) = saved
+    m, h = x.shape
+    c = P["aggr_w"].shape[0]
+    sink = GradSink(x.device)
+    linear_bwd_weight(operand(d_raw, c), operand(x, h), m, c, h, G["aggr_w"], G["aggr_b"], sink)
+    sink.flush()
+    return linear_bwd_data(d_raw, P["aggr_w"])
+
+
+# --------------------------------------------------------------------------------------------- links + CRPS
+def postprocess_fwd(raw, kind):
+    post = torch.empty_like(raw)
+    _lib.check(_lib.lib().rc_postprocess_fwd(raw.data_ptr(), post.data_ptr(), raw.shape[0], kind, _stream(raw)), "rc_postprocess_fwd")
+    return post
+
+
+def postprocess_bwd(raw, d_post, kind):
+    d_raw = torch.empty_like(raw)
+    _lib.check(_lib.lib().rc_postprocess_bwd(raw.data_ptr(), d_post.data_ptr(), d_raw.data_ptr(), raw.shape[0], kind, _stream(raw)),
+               "rc_postprocess_bwd")
+    return d_raw
+
+
+def crps_fwd_bwd(pred, y, kind, *, raw_input=False, u=0.0, xi=0.5, t=5.0, need_grad=True):
+    """(loss float64 [1], d_pred or None, n_valid int32 [1]); d_pred already carries the 1/n_valid of the mean."""
+    L = _lib.lib()
+    m = pred.shape[0]
+    dev = pred.device
+    ws_bytes = int(L.rc_crps_workspace(m))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    n_valid = torch.empty(1, dtype=torch.int32, device=dev)
+    d_pred = torch.empty_like(pred) if need_grad else None
+    _lib.check(L.rc_crps_fwd_bwd(pred.data_ptr(), y.data_ptr(), _lib.ptr(d_pred), loss.data_ptr(), n_valid.data_ptr(), m, kind,
+                                 int(raw_input), float(u), float(xi), float(t), ws.data_ptr(), ws_bytes, _stream(pred)),
+               "rc_crps_fwd_bwd")
+    return loss, d_pred, n_valid

@@ -1,0 +1,120 @@
+"""CUDA-backed mirror of models/gnn.py: same classes, constructor signatures, attribute names and
+state_dict layout (60 keys at 4 layers), so train.py / eval.py, params.json and the
+bare-state_dict .ckpt work unchanged.  The torch.nn modules below only OWN the parameters and
+buffers; every forward / backward runs in librc_b200.so through functional.py.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.nn import Linear, ModuleList, ReLU
+
+from .. import functional as F_rc
+from ..graph import graph_of
+from .loss import MixedLoss, MixedNormalCRPS, NormalCRPS
+from .model_utils import PostProcess
+
+
+class GINEConv(nn.Module):
+    """Parameter holder with torch_geometric.nn.GINEConv's layout: `nn` (the node MLP), `lin`
+    (Linear(edge_dim, in_channels)) and `eps` (Parameter [1], initial value 0 when train_eps)."""
+
+    def __init__(self, nn_module: nn.Sequential, train_eps: bool = True, edge_dim: int = 1):
+        super().__init__()
+        if edge_dim != 1:
+            raise NotImplementedError("the station graph carries one edge feature (utils/data.py:272-275)")
+        self.nn = nn_module
+        self.lin = Linear(edge_dim, nn_module[0].in_features)
+        if train_eps:
+            self.eps = nn.Parameter(torch.zeros(1))
+        else:
+            self.register_buffer("eps", torch.zeros(1))
+
+    def layer(self, x, graph, first: bool):
+        bn = self.nn[1]
+        return F_rc.GineLayerFn.apply(x, graph, first, self.training and bn.training, bn.running_mean, bn.running_var,
+                                      bn.num_batches_tracked, self.eps, self.lin.weight, self.lin.bias,
+                                      self.nn[0].weight, self.nn[0].bias, bn.weight, bn.bias, self.nn[3].weight,
+                                      self.nn[3].bias)
+
+
+class ResGnn(nn.Module):
+    """models/gnn.py:10-45."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_layers: int, hidden_channels: int):
+        super().__init__()
+        assert num_layers > 0, "num_layers must be > 0."
+        self.convolutions = ModuleList()
+        for _ in range(num_layers):
+            mlp = nn.Sequential(Linear(in_channels, hidden_channels), nn.BatchNorm1d(hidden_channels), ReLU(),
+                                Linear(hidden_channels, hidden_channels))    # every layer is H -> H (:31-32 has no effect)
+            self.convolutions.append(GINEConv(mlp, train_eps=True, edge_dim=1))
+        self.relu = ReLU()
+
+    def forward(self, x, edge_index=None, edge_attr=None, graph=None):
+        if graph is None:
+            from ..graph import _GLOBAL_CACHE
+            graph = _GLOBAL_CACHE.get(edge_index, edge_attr, int(x.shape[0]))
+        x = x.float()
+        for i, conv in enumerate(self.convolutions):
+            x = conv.layer(x, graph, first=(i == 0))
+        return x
+
+
+class DeepSetEncoder(nn.Module):
+    """models/gnn.py:48-68: rho(sum over members of phi(member))."""
+
+    def __init__(self, ensemble_in_dim, hidden_channels, out_channels):
+        super().__init__()
+        self.phi = nn.Sequential(nn.Linear(ensemble_in_dim, hidden_channels), nn.ReLU(),
+                                 nn.Linear(hidden_channels, hidden_channels))
+        self.rho = nn.Sequential(nn.Linear(hidden_channels, hidden_channels), nn.ReLU(),
+                                 nn.Linear(hidden_channels, out_channels))
+
+    def forward(self, ensemble_feats):
+        if ensemble_feats.dim() != 3:
+            raise ValueError(f"ensemble must be [N, E, F], got {tuple(ensemble_feats.shape)}")
+        return F_rc.DeepSetsFn.apply(ensemble_feats, self.phi[0].weight, self.phi[0].bias, self.phi[2].weight,
+                                     self.phi[2].bias, self.rho[0].weight, self.rho[0].bias, self.rho[2].weight,
+                                     self.rho[2].bias)
+
+
+class GNN(nn.Module):
+    """models/gnn.py:71-141."""
+
+    def __init__(self, in_channels, hidden_channels_gnn, out_channels_gnn, num_layers_gnn, optimizer_class,
+                 optimizer_params, loss, grad_u=False, u=0.5, xi=0.5):
+        super().__init__()
+        self.loss, self.grad_u, self.u, self.xi = loss, grad_u, u, xi
+        if loss == "NormalCRPS":
+            self.loss_fn, self.out_channels = NormalCRPS(), 2
+        elif loss == "MixedNormalCRPS":
+            self.loss_fn, self.out_channels = MixedNormalCRPS(), 3
+        elif loss == "MixedLoss":
+            if grad_u == "True":                       # params.json stores the string (models/gnn.py:98)
+                self.loss_fn, self.out_channels = MixedLoss(grad_u=True, xi=xi), 5
+            else:
+                self.loss_fn, self.out_channels = MixedLoss(grad_u=False, u=u, xi=xi), 4
+        else:
+            raise ValueError(f"unknown loss {loss!r}")
+        self.deepset = DeepSetEncoder(in_channels, hidden_channels_gnn, hidden_channels_gnn)
+        self.dim_red = Linear(in_channels + hidden_channels_gnn, hidden_channels_gnn)
+        self.conv = ResGnn(in_channels=hidden_channels_gnn, hidden_channels=hidden_channels_gnn,
+                           out_channels=hidden_channels_gnn, num_layers=num_layers_gnn)
+        self.aggr = nn.Linear(out_channels_gnn, self.out_channels)
+        self.postprocess = PostProcess(self.loss, self.grad_u)
+        self.optimizer_class, self.optimizer_params = optimizer_class, optimizer_params
+
+    def raw_head(self, data):
+        """Head outputs before the links (what the fused train step feeds to the CRPS kernel)."""
+        graph = graph_of(data)
+        emb = self.deepset(data.ensemble)
+        node = F_rc.DimRedFn.apply(data.x, emb, self.dim_red.weight, self.dim_red.bias)
+        x = self.conv(node, graph=graph)
+        return F_rc.HeadFn.apply(x, self.aggr.weight, self.aggr.bias)
+
+    def forward(self, data):
+        return self.postprocess(self.raw_head(data))
+
+    def configure_optimizers(self):
+        return self.optimizer_class(self.parameters(), **self.optimizer_params)

@@ -1,0 +1,72 @@
+"""Dataset seam.  `EUPPBench` keeps the reference constructor (utils/dataset.py:29-38) and loads the
+processed split files the reference writes (`torch.save((data, slices))`, utils/dataset.py:174-182) when
+they exist; it cannot download / process raw Zarr data (no network; xarray/zarr/geopy are not in the
+image) and says so.  `SyntheticEUPPBench` generates the SURVEY.md 8d data of the same shapes."""
+from __future__ import annotations
+
+import os
+from typing import List
+
+import torch
+
+from ..graph import radius_graph
+from ..pyg_compat.data import Data
+from . import synthetic as syn
+from .data import make_graphs
+
+
+class SyntheticEUPPBench:
+    """`n_dates` station graphs of the reference shape sharing one radius graph."""
+
+    def __init__(self, n_dates: int = 64, num_stations: int = 122, members: int = 11, feats: int = 35,
+                 max_dist: float = 100.0, box: float = 600.0, seed: int = 42):
+        coords = syn.station_coords(num_stations, box, seed=0)
+        self.edge_index, self.edge_attr = radius_graph(syn.distance_matrix(coords), max_dist)
+        x, ens = syn.node_features(n_dates * num_stations, members, feats, seed=seed)
+        y = syn.log_precip_targets(n_dates * num_stations, seed=seed)
+        self.graphs: List[Data] = make_graphs(x, ens, y, self.edge_index, self.edge_attr, num_stations)
+
+    def __len__(self):
+        return len(self.graphs)
+
+    def __getitem__(self, i):
+        return self.graphs[i]
+
+
+class EUPPBench:
+    available_splits = ["train_rf", "test_rf", "test_f"]
+
+    def __init__(self, root_raw: str, root_processed: str, leadtime: str = "24h", max_dist: float = 100.0,
+                 split: str = "train_rf", transform=None, pre_transform=None):
+        if split not in self.available_splits:
+            raise ValueError(f"split must be one of {self.available_splits}, got {split}")
+        self.leadtime, self.max_dist, self.split = leadtime, max_dist, split
+        self.root_raw, self.root_processed = root_raw, root_processed
+        path = os.path.join(root_processed, f"EUPPBench_{leadtime}_{split}.pt")
+        if not os.path.isfile(path):
+            raise FileNotFoundError(
+                f"{path} not found. Processing raw EUPPBench Zarr archives (utils/dataset.py:95-182) needs network "
+                "access and xarray/zarr/geopy, which this build does not have; use SyntheticEUPPBench or copy the "
+                "reference's processed .pt files here.")
+        data, slices = torch.load(path, weights_only=False)
+        self.graphs = self._unpack(data, slices)
+
+    @staticmethod
+    def _unpack(data, slices) -> List[Data]:
+        get = (lambda k: data[k]) if isinstance(data, dict) else (lambda k: getattr(data, k))
+        n = len(slices["x"]) - 1
+        e0, e1 = int(slices["edge_index"][0]), int(slices["edge_index"][1])
+        edge_index = get("edge_index")[:, e0:e1].contiguous()       # static graph: share the first copy
+        edge_attr = get("edge_attr")[int(slices["edge_attr"][0]):int(slices["edge_attr"][1])].contiguous()
+        out = []
+        for i in range(n):
+            d = Data(**{k: get(k)[int(slices[k][i]):int(slices[k][i + 1])] for k in ("x", "ensemble", "y")},
+                     edge_index=edge_index, edge_attr=edge_attr)
+            out.append(d)
+        return out
+
+    def __len__(self):
+        return len(self.graphs)
+
+    def __getitem__(self, i):
+        return self.graphs[i]

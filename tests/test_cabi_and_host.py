@@ -1,0 +1,147 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rc_b200.h declares; the
+host-side graph builders are bit-exact against the reference fixtures and the oracle; the loader seam
+behaves like PyG's collate.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import graph as og
+from raincast_gnn_b200 import _lib, graph as G
+from raincast_gnn_b200.utils import synthetic as syn
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rc_b200.h")).read()
+    declared = set(re.findall(r"\b(rc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 28
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in rc_b200.h but not exported"
+    _lib.lib()
+    assert set(_lib.EXPORTS) == declared, set(_lib.EXPORTS) ^ declared
+    assert _lib.lib().rc_version() == 100
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors must have the C layout (64-bit): spot-check sizes against hand-computed values."""
+    assert ctypes.sizeof(_lib.rc_csr) == 80
+    assert ctypes.sizeof(_lib.rc_operand) == 80
+    assert ctypes.sizeof(_lib.rc_reduce_seg) == 48
+
+
+def test_errors_are_reported_not_swallowed():
+    L = _lib.lib()
+    assert L.rc_gemm_run(None, None) == 1
+    assert b"rc_gemm_run" in L.rc_last_error()
+    with pytest.raises(_lib.RcError):
+        _lib.check(L.rc_crps_fwd_bwd(None, None, None, None, None, 4, 3, 0, 0.0, 0.5, 5.0, None, 0, None), "rc_crps_fwd_bwd")
+    with pytest.raises(_lib.RcError):        # CPU tensors never reach a kernel
+        _lib.require_cuda(torch.zeros(3))
+
+
+@pytest.mark.parametrize("name,n,box,md", [("ref122_d100", 122, 600.0, 100.0), ("ref122_d1", 122, 600.0, 1.0),
+                                           ("n7_d300", 7, 600.0, 300.0), ("n40_d150", 40, 600.0, 150.0)])
+def test_radius_graph_host_bit_exact(golden_graph, name, n, box, md):
+    coords = syn.station_coords(n, box, seed=0)
+    for ei, ea in (G.radius_graph(syn.distance_matrix(coords), md), G.radius_graph_from_coords(coords, md)):
+        assert ei.dtype == torch.int64 and ea.dtype == torch.float32 and ea.shape == (ei.shape[1], 1)
+        assert np.array_equal(ei.numpy(), golden_graph[f"{name}.edge_index"])
+        assert np.array_equal(ea.numpy().view(np.uint32), golden_graph[f"{name}.edge_attr"].view(np.uint32))
+
+
+def test_radius_graph_asymmetric_and_empty(golden_graph):
+    ei, ea = G.radius_graph(golden_graph["asym23.dist"], 120.0)
+    assert np.array_equal(ei.numpy(), golden_graph["asym23.edge_index"])
+    assert np.array_equal(ea.numpy(), golden_graph["asym23.edge_attr"])
+    ei, ea = G.radius_graph(np.zeros((0, 0), np.float32), 1.0)
+    assert ei.shape == (2, 0) and ea.shape == (0, 1)
+
+
+@pytest.mark.parametrize("name,batch", [("ref122_d100", 8), ("asym23", 3), ("ref122_d1", 2)])
+def test_csr_host_matches_oracle(golden_graph, name, batch):
+    ei, ea = torch.from_numpy(golden_graph[f"{name}.edge_index"]), torch.from_numpy(golden_graph[f"{name}.edge_attr"])
+    n = int(ei.max()) + 1
+    eib, eab = G.collate_static(ei, ea, n, batch)
+    oei, oea = og.collate_edges(ei.numpy(), ea.numpy(), n, batch)
+    assert np.array_equal(eib.numpy(), oei) and np.array_equal(eab.numpy(), oea)
+    sg = G.build_station_graph(eib, eab, n * batch)
+    for k, v in og.csr_layout(oei, oea, n * batch).items():
+        assert np.array_equal(getattr(sg, k).numpy().view(np.uint32), v.view(np.uint32)), k
+    assert torch.equal(sg.edge_index(), eib)
+
+
+def test_scaled_graph_edge_count():
+    n = 100_000
+    ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
+    assert ei.shape[1] == 2_978_560          # SURVEY.md 8d [probe]
+    assert float(ea.min()) == 1.0
+
+
+def test_coords_graph_matches_kdtree():
+    from scipy.spatial import cKDTree
+    n, r = 3000, 25.0
+    coords = syn.station_coords(n, 1000.0, seed=5)
+    ei, _ = G.radius_graph_from_coords(coords, r)
+    pairs = cKDTree(coords).query_pairs(r * 1.0001, output_type="ndarray")
+    d = np.sqrt(((coords[pairs[:, 0]] - coords[pairs[:, 1]]) ** 2).sum(-1)).astype(np.float32)
+    pairs = pairs[d <= np.float32(r)]
+    want = set(map(tuple, pairs)) | set((b, a) for a, b in pairs)
+    got = set(map(tuple, ei[:, :-n].T.tolist()))
+    assert got == want
+    assert torch.equal(ei[:, -n:], torch.arange(n).repeat(2, 1))
+
+
+def test_loader_collates_like_pyg_and_caches_the_graph():
+    from oracle import pyg as opyg
+    from raincast_gnn_b200.pyg_compat import Batch, DataLoader
+    from raincast_gnn_b200.utils.dataset import SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=10, num_stations=20, members=3, feats=4, max_dist=250.0)
+    loader = DataLoader(ds, batch_size=4, shuffle=False)
+    assert len(loader) == 3
+    batches = list(loader)
+    ref = opyg.Batch.from_data_list([opyg.Data(x=d.x, ensemble=d.ensemble, edge_index=d.edge_index, edge_attr=d.edge_attr, y=d.y)
+                                     for d in ds.graphs[:4]])
+    b0 = batches[0]
+    for k in ("x", "ensemble", "edge_index", "edge_attr", "batch", "ptr"):
+        assert torch.equal(getattr(b0, k), getattr(ref, k)), k
+    assert torch.equal(torch.nan_to_num(b0.y, nan=-99.0), torch.nan_to_num(ref.y, nan=-99.0))
+    assert batches[1].station_graph is b0.station_graph            # static graph: one CSR per batch size
+    assert batches[2].station_graph is not b0.station_graph and batches[2].x.shape[0] == 40
+    assert torch.equal(b0.station_graph.edge_index(), b0.edge_index)
+
+
+def test_split_graph_and_compat_install():
+    from raincast_gnn_b200 import pyg_compat
+    from raincast_gnn_b200.utils.data import split_graph
+    from raincast_gnn_b200.utils.dataset import EUPPBench, SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=1, members=51)
+    parts = split_graph(ds[0], True)
+    assert len(parts) == 5 and all(p.ensemble.shape[1] == 10 for p in parts)
+    assert torch.equal(parts[2].ensemble, ds[0].ensemble[:, 20:30])
+    assert parts[0].edge_index is ds[0].edge_index
+    with pytest.raises(ValueError):
+        EUPPBench("raw", "processed", split="bogus")
+    with pytest.raises(FileNotFoundError):
+        EUPPBench("raw", "processed", split="train_rf")
+    pyg_compat.install()
+    from torch_geometric.loader import DataLoader  # noqa: F401
+
+
+def test_model_state_dict_layout_and_ctor_errors(golden_model):
+    from raincast_gnn_b200.models import GNN, MixedLoss, ResGnn
+    m = GNN(35, 128, 128, 4, torch.optim.AdamW, {"lr": 1e-4}, "MixedLoss", "True", 1.71, 0.5)
+    assert list(m.state_dict().keys()) == list(golden_model["ref_mixed_u.keys"])
+    assert sum(p.numel() for p in m.parameters()) == 209_929
+    assert m.out_channels == 5 and isinstance(m.loss_fn, MixedLoss) and m.loss_fn.grad_u is True
+    assert GNN(35, 128, 128, 4, None, None, "MixedLoss", "False", 1.71, 0.5).out_channels == 4
+    assert GNN(35, 128, 128, 4, None, None, "MixedNormalCRPS").out_channels == 3
+    assert GNN(35, 128, 128, 4, None, None, "NormalCRPS").out_channels == 2
+    with pytest.raises(AssertionError):
+        ResGnn(8, 8, 0, 8)                                            # models/gnn.py:13
+    with pytest.raises(ValueError):
+        MixedLoss(grad_u=False, xi=1.0, u=1.0)
