@@ -134,7 +134,9 @@ def require_cuda(*tensors):
 
 
 def f32c(t: torch.Tensor) -> torch.Tensor:
-    """float32, contiguous view/copy of t."""
+    """float32, contiguous, 16-byte aligned view/copy of t (the kernels use 128-bit loads)."""
     if t.dtype != torch.float32:
         t = t.float()
-    return t if t.is_contiguous() else t.contiguous()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()

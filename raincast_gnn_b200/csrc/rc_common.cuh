@@ -27,6 +27,8 @@ inline int check_launch(const char* what) {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

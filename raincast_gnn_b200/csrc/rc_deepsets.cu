@@ -239,6 +239,7 @@ extern "C" int rc_deepsets_pool_fwd(const float* ens, const float* w1, const flo
   if (!ens || !w1 || !b1 || !pooled || num_nodes < 0 || members <= 0 || feats <= 0 || hidden <= 0)
     return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd: bad argument");
   if (num_nodes == 0) return RC_OK;
+  if (!aligned16(pooled) && hidden % 4 == 0) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd: pooled must be 16-byte aligned");
   const int f4 = (feats + 3) & ~3;
   const size_t smem = ((size_t)f4 * kDsCols + kDsCols + (size_t)kDsWarps * kDsMemberChunk * f4) * sizeof(float);
   if (smem > 200 * 1024) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd: feats=%d too large for the shared-memory tile", feats);
@@ -279,6 +280,7 @@ extern "C" int rc_deepsets_pool_bwd(const float* ens, const float* w1, const flo
                                     float* partials, int num_nodes, int members, int feats, int hidden, void* stream) {
   if (!ens || !w1 || !b1 || !d_pooled || !partials || num_nodes < 0 || members <= 0 || feats <= 0 || hidden <= 0)
     return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: bad argument");
+  if (!aligned16(d_pooled)) return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: d_pooled must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int kq = ceil_div(feats, 8);
   switch (kq) {

@@ -421,7 +421,6 @@ static int choose_rm(const rc_gemm* g) {
   return 1;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace rc
 

@@ -121,7 +121,7 @@ gine_aggr_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
   const int rows_per_block = kGineWarps * rpw;
   const float self_scale = 1.0f + __ldg(eps_ptr);
   float4 w4[CH], b4[CH], dw[CH], db[CH];
-  float deps = 0.f;
+  double deps = 0.0;   // <g, x> has heavy cancellation over M*H products: accumulate across rows in float64
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     const int cc = 4 * (sl + 32 * c);
@@ -138,7 +138,7 @@ gine_aggr_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
       xj[c] = ldg4(x + (size_t)row * hidden + cc);
       gj[c] = ldg4(g + (size_t)row * hidden + cc);
       acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      deps += gj[c].x * xj[c].x + gj[c].y * xj[c].y + gj[c].z * xj[c].z + gj[c].w * xj[c].w;
+      deps += (double)(gj[c].x * xj[c].x + gj[c].y * xj[c].y + gj[c].z * xj[c].z + gj[c].w * xj[c].w);
     }
     const int beg = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
     int q = beg;
@@ -199,7 +199,7 @@ gine_aggr_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, c
   }
   // lanes of one sub-warp hold disjoint column slices of the same rows: sum their <g, x> partials
   for (int o = lpr >> 1; o > 0; o >>= 1) deps += __shfl_xor_sync(0xffffffffu, deps, o);
-  if (sl == 0) red_eps[slot] = deps;
+  if (sl == 0) red_eps[slot] = (float)deps;
   __syncthreads();
   float* out = partials + (size_t)blockIdx.x * 3 * hidden;
   for (int j = threadIdx.x; j < 2 * hidden; j += blockDim.x) {
@@ -257,6 +257,7 @@ extern "C" int rc_gine_aggr_fwd(const float* x, const int32_t* rowptr, const int
   if (!x || !rowptr || !col || !attr || !w_edge || !b_edge || !eps || !h || num_nodes < 0)
     return fail(RC_ERR_ARG, "rc_gine_aggr_fwd: null pointer");
   if (!gine_shape(hidden, &sh)) return fail(RC_ERR_ARG, "rc_gine_aggr_fwd: hidden=%d unsupported (need 4|H, H/4 a power of two below 128, 128|H up to 512)", hidden);
+  if (!aligned16(x) || !aligned16(h) || !aligned16(w_edge) || !aligned16(b_edge)) return fail(RC_ERR_ARG, "rc_gine_aggr_fwd: x, h, w_edge, b_edge must be 16-byte aligned");
   if (num_nodes == 0) return RC_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = ceil_div(num_nodes, kGineWarps * sh.rpw);
@@ -284,6 +285,9 @@ extern "C" int rc_gine_aggr_bwd(const float* g, const float* x, const int32_t* t
   if (!g || !x || !t_rowptr || !t_dst || !t_attr || !w_edge || !b_edge || !eps || !dx || !partials || num_nodes < 0)
     return fail(RC_ERR_ARG, "rc_gine_aggr_bwd: null pointer");
   if (!gine_shape(hidden, &sh)) return fail(RC_ERR_ARG, "rc_gine_aggr_bwd: hidden=%d unsupported", hidden);
+  if (!aligned16(g) || !aligned16(x) || !aligned16(dx) || !aligned16(w_edge) || !aligned16(b_edge) || !aligned16(partials) ||
+      (addend && !aligned16(addend)))
+    return fail(RC_ERR_ARG, "rc_gine_aggr_bwd: g, x, dx, addend, w_edge, b_edge, partials must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = rc_gine_aggr_bwd_nblocks(num_nodes, hidden);
   const int rpb = kGineWarps * sh.rpw;

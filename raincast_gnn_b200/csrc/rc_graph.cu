@@ -133,14 +133,15 @@ extern "C" int rc_radius_graph_coords_fill_host(const double* xy, int n, double 
 }
 
 // ------------------------------------------------------------------------------------------------ host: CSR layout
-static bool csr_ptrs_ok(const rc_csr* o) {
-  return o && o->rowptr && o->col && o->attr && o->perm && o->t_rowptr && o->t_dst && o->t_attr && o->t_perm &&
-         o->t_slot && o->rev;
+static bool csr_ptrs_ok(const rc_csr* o, int64_t n_edges) {
+  if (!o || !o->rowptr || !o->t_rowptr) return false;
+  if (n_edges == 0) return true;   // an empty graph has no per-edge arrays
+  return o->col && o->attr && o->perm && o->t_dst && o->t_attr && o->t_perm && o->t_slot && o->rev;
 }
 
 extern "C" int rc_csr_build_host(const int64_t* edge_index, const float* edge_attr, int64_t n_edges, int num_nodes,
                                  const rc_csr* out) {
-  if (!edge_index || !edge_attr || !csr_ptrs_ok(out) || n_edges < 0 || num_nodes < 0)
+  if (((!edge_index || !edge_attr) && n_edges > 0) || !csr_ptrs_ok(out, n_edges) || n_edges < 0 || num_nodes < 0)
     return fail(RC_ERR_ARG, "rc_csr_build_host: bad argument");
   if (n_edges > 0x7fffffffLL) return fail(RC_ERR_ARG, "rc_csr_build_host: more than 2^31-1 edges");
   const int64_t* src = edge_index;
@@ -287,7 +288,7 @@ extern "C" size_t rc_csr_build_workspace(int64_t n_edges, int num_nodes) {
 
 extern "C" int rc_csr_build(const int64_t* edge_index, const float* edge_attr, int64_t n_edges, int num_nodes,
                             const rc_csr* out, void* workspace, size_t workspace_bytes, int32_t* err_flag, void* stream) {
-  if (!edge_index || !edge_attr || !csr_ptrs_ok(out) || !workspace || !err_flag || n_edges < 0 || num_nodes < 0)
+  if (((!edge_index || !edge_attr) && n_edges > 0) || !csr_ptrs_ok(out, n_edges) || !workspace || !err_flag || n_edges < 0 || num_nodes < 0)
     return fail(RC_ERR_ARG, "rc_csr_build: bad argument");
   if (n_edges > 0x7fffffffLL) return fail(RC_ERR_ARG, "rc_csr_build: more than 2^31-1 edges");
   if (workspace_bytes < rc_csr_build_workspace(n_edges, num_nodes)) return fail(RC_ERR_WORKSPACE, "rc_csr_build: workspace too small");

@@ -1,0 +1,193 @@
+"""Graphed training step: the explicit kernel schedule of one train.py iteration (train.py:61-71)
+
+    H2D batch -> DeepSets -> dim_red -> L x GINE layer -> head -> links+CRPS (value and gradient)
+              -> backward of every block -> [NCCL all-reduce of the flat gradient] -> fused AdamW
+
+captured once in a CUDA graph and replayed, with parameters, gradients and Adam moments in flat buffers.
+No autograd, no per-step Python dispatch, no host sync: the loss stays on the device (train.py's per-step
+`loss.item()` becomes one read per epoch).  Data-parallel semantics are DDP's: per-rank BatchNorm
+statistics, per-rank mean over valid nodes, mean of rank gradients; the 0.84 MB gradient
+bucket is all-reduced once per step over NVLink and the 1/world factor is folded into the AdamW kernel.
+
+The module keeps owning the parameters: `model.parameters()` become views of the flat buffer, so
+state_dict() / .ckpt saving keep working while the engine trains.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from . import kernels as K
+from .graph import StationGraph
+from .models.model_utils import loss_kind
+
+
+_ALIGN = 4      # floats: every parameter view starts on a 16-byte boundary (the kernels use 128-bit loads)
+
+
+def _padded(n: int) -> int:
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+def _flatten_into(tensors, flat):
+    off = 0
+    views = []
+    for t in tensors:
+        n = t.numel()
+        views.append(flat[off:off + n].view(t.shape))
+        off += _padded(n)
+    return views
+
+
+class TrainEngine:
+    def __init__(self, model, graph: StationGraph, num_nodes: int, members: int, feats: int, *, lr: float = 1e-4,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None,
+                 use_cuda_graph: bool = True):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.RcError("TrainEngine needs the model on a CUDA device (there is no CPU path)")
+        self.model, self.graph, self.device = model, graph.to(dev), dev
+        self.m, self.members, self.feats = num_nodes, members, feats
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.kind = loss_kind(model.loss, model.grad_u)
+        self.u_fixed = 0.0 if model.grad_u == "True" else float(model.u)
+        self.xi = float(model.xi)
+        self.t = float(getattr(model.loss_fn, "t", 5.0))
+        # ---- flat parameter / gradient / moment buffers (parameters become views)
+        params = list(model.parameters())
+        self.names = [n for n, _ in model.named_parameters()]
+        total = sum(_padded(p.numel()) for p in params)      # padding stays zero: zero gradient, zero update
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        views = _flatten_into(params, self.flat_p)
+        with torch.no_grad():
+            for p, v in zip(params, views):
+                v.copy_(p.detach().float())
+                p.data = v
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = dict(zip(self.names, _flatten_into(params, self.flat_g)))
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.step_count = torch.zeros((), dtype=torch.int64, device=dev)
+        self.n_params = total
+        # ---- static inputs / outputs
+        self.x = torch.zeros((num_nodes, feats), dtype=torch.float32, device=dev)
+        self.ens = torch.zeros((num_nodes, members, feats), dtype=torch.float32, device=dev)
+        self.y = torch.zeros((num_nodes,), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._blocks = self._bind(model)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
+
+    # ------------------------------------------------------------------ parameter dictionaries for kernels.py
+    def _bind(self, model):
+        P = dict(model.named_parameters())
+        G = self.grads
+        B = dict(model.named_buffers())
+
+        def pick(src, mapping):
+            return {k: src[v] for k, v in mapping.items()}
+        ds_map = {"phi0_w": "deepset.phi.0.weight", "phi0_b": "deepset.phi.0.bias", "phi2_w": "deepset.phi.2.weight",
+                  "phi2_b": "deepset.phi.2.bias", "rho0_w": "deepset.rho.0.weight", "rho0_b": "deepset.rho.0.bias",
+                  "rho2_w": "deepset.rho.2.weight", "rho2_b": "deepset.rho.2.bias"}
+        dr_map = {"dimred_w": "dim_red.weight", "dimred_b": "dim_red.bias"}
+        hd_map = {"aggr_w": "aggr.weight", "aggr_b": "aggr.bias"}
+        layers = []
+        for i in range(len(model.conv.convolutions)):
+            pre = f"conv.convolutions.{i}."
+            lmap = {"eps": pre + "eps", "lin_w": pre + "lin.weight", "lin_b": pre + "lin.bias", "nn0_w": pre + "nn.0.weight",
+                    "nn0_b": pre + "nn.0.bias", "bn_w": pre + "nn.1.weight", "bn_b": pre + "nn.1.bias",
+                    "nn3_w": pre + "nn.3.weight", "nn3_b": pre + "nn.3.bias"}
+            lp = pick(P, lmap)
+            lp.update(bn_rm=B[pre + "nn.1.running_mean"], bn_rv=B[pre + "nn.1.running_var"],
+                      bn_nbt=B[pre + "nn.1.num_batches_tracked"])
+            layers.append((lp, pick(G, lmap)))
+        return {"ds": (pick(P, ds_map), pick(G, ds_map)), "dr": (pick(P, dr_map), pick(G, dr_map)),
+                "layers": layers, "head": (pick(P, hd_map), pick(G, hd_map))}
+
+    # ------------------------------------------------------------------ one forward + loss + backward (no optimiser)
+    def _fwd_bwd(self):
+        blk = self._blocks
+        Pd, Gd = blk["ds"]
+        emb, s_ds = K.deepsets_fwd(Pd, self.ens)
+        Pr, Gr = blk["dr"]
+        node, s_dr = K.dimred_fwd(Pr, self.x, emb)
+        saved = []
+        h = node
+        for i, (Pl, _) in enumerate(blk["layers"]):
+            h, s = K.gine_layer_fwd(Pl, h, self.graph, first=(i == 0), training=True)
+            saved.append(s)
+        Ph, Gh = blk["head"]
+        raw, s_h = K.head_fwd(Ph, h)
+        loss, d_raw, _ = K.crps_fwd_bwd(raw, self.y, self.kind, raw_input=True, u=self.u_fixed, xi=self.xi, t=self.t)
+        self.loss.copy_(loss)
+        self.loss_sum.add_(loss)
+        d = K.head_bwd(Ph, s_h, d_raw, Gh)
+        for i in reversed(range(len(blk["layers"]))):
+            Pl, Gl = blk["layers"][i]
+            d = K.gine_layer_bwd(Pl, saved[i], self.graph, d, Gl, first=(i == 0), training=True)
+        d_emb = K.dimred_bwd(Pr, s_dr, d, Gr)
+        K.deepsets_bwd(Pd, s_ds, d_emb, Gd)
+
+    def _optimizer(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        _lib.check(_lib.lib().rc_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                            self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.n_params, self.lr,
+                                            self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world,
+                                            torch.cuda.current_stream(self.device).cuda_stream), "rc_adamw_step")
+
+    def capture(self):
+        """Warm up (allocator, lazy kernel attributes) on a side stream, then capture fwd+bwd in a CUDA graph.
+        BatchNorm running statistics and Adam state are restored afterwards, so capture has no training effect."""
+        snap = {k: v.clone() for k, v in self.model.state_dict().items()}
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._fwd_bwd()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if self.use_cuda_graph:
+            self._graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(self._graph):
+                self._fwd_bwd()
+            self.kernels_per_step = _lib.launch_count() - before
+        else:
+            before = _lib.launch_count()
+            self._fwd_bwd()
+            self.kernels_per_step = _lib.launch_count() - before
+        torch.cuda.synchronize(self.device)
+        with torch.no_grad():
+            for k, v in self.model.state_dict().items():
+                v.copy_(snap[k])
+        self.loss_sum.zero_()
+        self.flat_g.zero_()
+        return self
+
+    # ------------------------------------------------------------------ public
+    def load_batch(self, x, ensemble, y, non_blocking: bool = True):
+        """Copy one batch (host pinned or device tensors) into the static input buffers."""
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.ens.copy_(ensemble, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+
+    def step(self):
+        """One training step on the batch in the static buffers; returns the device-resident loss (float64 [1])."""
+        if self._graph is None and self.use_cuda_graph:
+            self.capture()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._fwd_bwd()
+        self._optimizer()
+        return self.loss
+
+    @property
+    def launches_per_step(self) -> int:
+        """librc kernels per step: the captured fwd+bwd plus the two AdamW launches."""
+        return int(self.kernels_per_step or 0) + 2

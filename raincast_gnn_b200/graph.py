@@ -59,7 +59,8 @@ def _alloc(num_nodes: int, num_edges: int, device) -> dict:
     out = {}
     for f in _FIELDS:
         n = num_nodes + 1 if f.endswith("rowptr") else num_edges
-        out[f] = torch.empty(n, dtype=torch.float32 if f in _FLOAT else torch.int32, device=device)
+        # at least one element of storage so that an empty graph still has non-null pointers
+        out[f] = torch.empty(max(n, 1), dtype=torch.float32 if f in _FLOAT else torch.int32, device=device)[:n]
     return out
 
 

@@ -88,7 +88,8 @@ def test_gemm_forward_layout(dev, m, n, k, rm):
     x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g), torch.randn(n, generator=g)
     want = torch.relu(x.double() @ w.double().T + 2.0 * b.double())
     y = torch.empty(m, n, device=dev)
-    K.gemm(m, n, k, K.operand(x.to(dev), k), K.operand(w.to(dev), k), y, n, bias=b.to(dev), bias_scale=2.0,
+    xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)          # keep the device tensors alive: operand() holds raw pointers
+    K.gemm(m, n, k, K.operand(xd, k), K.operand(wd, k), y, n, bias=bd, bias_scale=2.0,
            epi=K.RC_EPI_RELU, rows_per_warp=rm)
     assert rel_err(_np(y), want.numpy()) < TOL
 
@@ -102,8 +103,9 @@ def test_gemm_backward_data_layout(dev, m, n, k, rm):
     dy, w, aux = torch.randn(m, k, generator=g), torch.randn(k, n, generator=g), torch.randn(m, n, generator=g)
     want = (dy.double() @ w.double()) * (aux > 0)
     out = torch.empty(m, n, device=dev)
-    K.gemm(m, n, k, K.operand(dy.to(dev), k), K.operand(w.to(dev), n), out, n, b_layout=K.RC_B_RED,
-           epi=K.RC_EPI_MASK_POS, e_aux=aux.to(dev), ld_e_aux=n, rows_per_warp=rm)
+    dyd, wd, auxd = dy.to(dev), w.to(dev), aux.to(dev)
+    K.gemm(m, n, k, K.operand(dyd, k), K.operand(wd, n), out, n, b_layout=K.RC_B_RED,
+           epi=K.RC_EPI_MASK_POS, e_aux=auxd, ld_e_aux=n, rows_per_warp=rm)
     assert rel_err(_np(out), want.numpy()) < TOL
 
 
@@ -116,7 +118,8 @@ def test_gemm_weight_grad_layout(dev, m, n, k, splits, rm):
     dy, x = torch.randn(m, n, generator=g), torch.randn(m, k, generator=g)
     part = torch.empty(splits, n, k, device=dev)
     cs = torch.empty(splits, n, device=dev)
-    K.gemm(n, k, m, K.operand(dy.to(dev), n), K.operand(x.to(dev), k), part, k, a_layout=K.RC_A_RED, b_layout=K.RC_B_RED,
+    dyd, xd = dy.to(dev), x.to(dev)
+    K.gemm(n, k, m, K.operand(dyd, n), K.operand(xd, k), part, k, a_layout=K.RC_A_RED, b_layout=K.RC_B_RED,
            splits=splits, split_stride=n * k, colsum_a=cs, rows_per_warp=rm)
     assert rel_err(_np(part.double().sum(0)), (dy.double().T @ x.double()).numpy()) < TOL
     assert rel_err(_np(cs.double().sum(0)), dy.double().sum(0).numpy()) < TOL
@@ -175,8 +178,9 @@ def test_gemm_bn_stats_and_prologue(dev, m, h):
     words = math.ceil(h / 32)
     bits = torch.empty(m, words, dtype=torch.int32, device=dev)
     y = torch.empty(m, h, device=dev)
+    resd = res.to(dev)
     K.gemm(m, h, h, K.operand(t, h, K.RC_OP_BN_RELU, (mean, rstd, gam, bet)), K.operand(w2, h), y, h, bias=b2,
-           epi=K.RC_EPI_RELU_RES, res=res.to(dev), ld_res=h, bits_out=bits, ld_bits_out=words)
+           epi=K.RC_EPI_RELU_RES, res=resd, ld_res=h, bits_out=bits, ld_bits_out=words)
     assert rel_err(_np(y), y_ref.numpy()) < TOL
     got_bits = ((bits.cpu().to(torch.int64).unsqueeze(-1) >> torch.arange(32)) & 1).reshape(m, -1)[:, :h].bool()
     want_bits = o_ref > 0
@@ -329,7 +333,10 @@ def test_adamw_kernel_matches_torch(dev):
         gr = torch.randn(n) * (0.1 + it)
         ref.grad = gr.clone()
         opt.step()
-        _lib.check(L.rc_adamw_step(p.data_ptr(), gr.to(dev).data_ptr(), m1.data_ptr(), v.data_ptr(), step.data_ptr(), n, 1e-4, 0.9, 0.999,
+        grd = gr.to(dev)
+        _lib.check(L.rc_adamw_step(p.data_ptr(), grd.data_ptr(), m1.data_ptr(), v.data_ptr(), step.data_ptr(), n, 1e-4, 0.9, 0.999,
                                    1e-8, 0.01, 1.0, torch.cuda.current_stream().cuda_stream))
     assert int(step) == 5
-    assert rel_err(_np(p - p0.to(dev)), (ref.detach() - p0).numpy()) < 1e-5
+    assert rel_err(_np(p), ref.detach().numpy()) < 1e-6
+    # the update itself (~5e-4 on parameters of size ~1): limited by fp32 rounding of p, not by the kernel
+    assert rel_err(_np(p - p0.to(dev)), (ref.detach() - p0).numpy()) < 2e-3
