@@ -47,4 +47,13 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// rc_gine_wide.cu: large-graph path of the aggregation kernels (H >= 128, at least kRangedMinRows rows)
+constexpr int kRangedMinRows = 16384;
+int gine_ranged_grid(int m);
+int launch_gine_fwd_ranged(const float* x, const int* rowptr, const int* col, const float* attr, const float* w_edge,
+                           const float* b_edge, const float* eps, float* h, int m, int hidden, cudaStream_t s);
+int launch_gine_bwd_ranged(const float* g, const float* x, const int* t_rowptr, const int* t_dst, const float* t_attr,
+                           const float* w_edge, const float* b_edge, const float* eps, const float* addend, float* dx,
+                           float* partials, int m, int hidden, cudaStream_t s);
+
 }  // namespace rc

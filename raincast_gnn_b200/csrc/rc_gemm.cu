@@ -16,8 +16,8 @@ namespace rc {
 
 constexpr int kGemmThreads = 256;
 constexpr int kBN = 128;   // output columns per CTA
-constexpr int kRK = 32;    // reduction slice
-constexpr int kPadK = kRK + 4;
+// reduction slice RK: 32 (throughput regime) or 128 (small, latency-bound problems: one memory round trip
+// covers K = 128 instead of four)
 
 struct GemmP {
   rc_gemm g;
@@ -61,8 +61,9 @@ __device__ __forceinline__ float4 load_op4(const rc_operand& o, const float* bas
   return v;
 }
 
-template <int RM, int AL, int BL>
+template <int RM, int AL, int BL, int kRK>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmP p) {
+  constexpr int kPadK = kRK + 4;
   constexpr int BM = 8 * RM;
   constexpr int SA = (AL == RC_A_ROW) ? kPadK : (BM + 4);            // A tile row stride (floats)
   constexpr int A_ROWS = (AL == RC_A_ROW) ? BM : kRK;
@@ -373,8 +374,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmP p) {
   }
 }
 
-template <int RM, int AL, int BL>
+template <int RM, int AL, int BL, int kRK>
 static size_t gemm_smem_bytes() {
+  constexpr int kPadK = kRK + 4;
   constexpr int BM = 8 * RM;
   constexpr int SA = (AL == RC_A_ROW) ? kPadK : (BM + 4);
   constexpr int A_ROWS = (AL == RC_A_ROW) ? BM : kRK;
@@ -387,26 +389,35 @@ static size_t gemm_smem_bytes() {
   return need > cs ? need : cs;
 }
 
-template <int RM, int AL, int BL>
+template <int RM, int AL, int BL, int kRK>
 static int gemm_launch(const GemmP& p, dim3 grid, cudaStream_t s) {
   static bool attr_set = false;
-  const size_t smem = gemm_smem_bytes<RM, AL, BL>();
+  const size_t smem = gemm_smem_bytes<RM, AL, BL, kRK>();
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_kernel<RM, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm_kernel<RM, AL, BL, kRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  gemm_kernel<RM, AL, BL><<<grid, kGemmThreads, smem, s>>>(p);
+  gemm_kernel<RM, AL, BL, kRK><<<grid, kGemmThreads, smem, s>>>(p);
   return check_launch("gemm_kernel");
 }
 
 template <int AL, int BL>
-static int gemm_dispatch_rm(int rm, const GemmP& p, dim3 grid, cudaStream_t s) {
-  switch (rm) {
-    case 1: return gemm_launch<1, AL, BL>(p, grid, s);
-    case 2: return gemm_launch<2, AL, BL>(p, grid, s);
-    case 4: return gemm_launch<4, AL, BL>(p, grid, s);
-    default: return gemm_launch<8, AL, BL>(p, grid, s);
+static int gemm_dispatch_rm(int rm, int rk, const GemmP& p, dim3 grid, cudaStream_t s) {
+  if (AL == RC_A_ROW && rk == 128) {
+    if (rm == 1) return gemm_launch<1, AL, BL, 128>(p, grid, s);
+    return gemm_launch<2, AL, BL, 128>(p, grid, s);
   }
+  switch (rm) {
+    case 1: return gemm_launch<1, AL, BL, 32>(p, grid, s);
+    case 2: return gemm_launch<2, AL, BL, 32>(p, grid, s);
+    case 4: return gemm_launch<4, AL, BL, 32>(p, grid, s);
+    default: return gemm_launch<8, AL, BL, 32>(p, grid, s);
+  }
+}
+
+// slice length: the long slice only where it removes round trips (row-major A, tiny row tiles, K > 32)
+static int choose_rk(const rc_gemm* g, int rm) {
+  return (g->a_layout == RC_A_ROW && rm <= 2 && (g->k > 32 || g->k2 > 32) && g->splits <= 1) ? 128 : 32;
 }
 
 static int choose_rm(const rc_gemm* g) {
@@ -456,13 +467,14 @@ extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
   p.a2_vec = g->k2 > 0 ? vec_ok(g->a2, g->lda2) : 0;
   p.b2_vec = g->k2 > 0 ? vec_ok(g->b2, g->ldb2) : 0;
   p.d_vec = vec_ok(g->d, g->ldd) && (g->splits <= 1 || g->split_stride % 4 == 0);
-  p.tiles1 = ceil_div(g->k, kRK);
-  p.tiles2 = g->k2 > 0 ? ceil_div(g->k2, kRK) : 0;
   const int rm = choose_rm(g);
+  const int rk = choose_rk(g, rm);
+  p.tiles1 = ceil_div(g->k, rk);
+  p.tiles2 = g->k2 > 0 ? ceil_div(g->k2, rk) : 0;
   dim3 grid(ceil_div(g->m, 8 * rm), ceil_div(g->n, kBN), g->splits > 1 ? g->splits : 1);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (g->a_layout == RC_A_ROW && g->b_layout == RC_B_COL) return gemm_dispatch_rm<RC_A_ROW, RC_B_COL>(rm, p, grid, s);
-  if (g->a_layout == RC_A_ROW && g->b_layout == RC_B_RED) return gemm_dispatch_rm<RC_A_ROW, RC_B_RED>(rm, p, grid, s);
-  if (g->a_layout == RC_A_RED && g->b_layout == RC_B_RED) return gemm_dispatch_rm<RC_A_RED, RC_B_RED>(rm, p, grid, s);
+  if (g->a_layout == RC_A_ROW && g->b_layout == RC_B_COL) return gemm_dispatch_rm<RC_A_ROW, RC_B_COL>(rm, rk, p, grid, s);
+  if (g->a_layout == RC_A_ROW && g->b_layout == RC_B_RED) return gemm_dispatch_rm<RC_A_ROW, RC_B_RED>(rm, rk, p, grid, s);
+  if (g->a_layout == RC_A_RED && g->b_layout == RC_B_RED) return gemm_dispatch_rm<RC_A_RED, RC_B_RED>(rm, rk, p, grid, s);
   return fail(RC_ERR_ARG, "rc_gemm_run: layout combination (A red-major, B col) is not instantiated");
 }

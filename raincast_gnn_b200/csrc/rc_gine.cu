@@ -260,6 +260,7 @@ extern "C" int rc_gine_aggr_fwd(const float* x, const int32_t* rowptr, const int
   if (!aligned16(x) || !aligned16(h) || !aligned16(w_edge) || !aligned16(b_edge)) return fail(RC_ERR_ARG, "rc_gine_aggr_fwd: x, h, w_edge, b_edge must be 16-byte aligned");
   if (num_nodes == 0) return RC_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (sh.lpr == 32 && num_nodes >= kRangedMinRows) return launch_gine_fwd_ranged(x, rowptr, col, attr, w_edge, b_edge, eps, h, num_nodes, hidden, s);
   const int grid = ceil_div(num_nodes, kGineWarps * sh.rpw);
   switch (sh.ch) {
     case 1: gine_aggr_fwd_kernel<1><<<grid, kGineThreads, 0, s>>>(x, rowptr, col, attr, w_edge, b_edge, eps, h, num_nodes, hidden, sh.lpr); break;
@@ -273,6 +274,7 @@ extern "C" int rc_gine_aggr_fwd(const float* x, const int32_t* rowptr, const int
 extern "C" int rc_gine_aggr_bwd_nblocks(int num_nodes, int hidden) {
   GineShape sh;
   if (!gine_shape(hidden, &sh) || num_nodes < 0) return -1;
+  if (sh.lpr == 32 && num_nodes >= kRangedMinRows) return gine_ranged_grid(num_nodes);
   const int nb = ceil_div(num_nodes > 0 ? num_nodes : 1, kGineWarps * sh.rpw);
   const int cap = kNumSMs * 8;
   return nb < cap ? nb : cap;
@@ -290,6 +292,8 @@ extern "C" int rc_gine_aggr_bwd(const float* g, const float* x, const int32_t* t
     return fail(RC_ERR_ARG, "rc_gine_aggr_bwd: g, x, dx, addend, w_edge, b_edge, partials must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = rc_gine_aggr_bwd_nblocks(num_nodes, hidden);
+  if (sh.lpr == 32 && num_nodes >= kRangedMinRows)
+    return launch_gine_bwd_ranged(g, x, t_rowptr, t_dst, t_attr, w_edge, b_edge, eps, addend, dx, partials, num_nodes, hidden, s);
   const int rpb = kGineWarps * sh.rpw;
   const size_t smem = ((size_t)rpb * 2 * hidden + rpb) * sizeof(float);
 #define RC_LAUNCH_BWD(CHV)                                                                                         \

@@ -79,6 +79,7 @@ class TrainEngine:
         self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         self._blocks = self._bind(model)
         self.use_cuda_graph = use_cuda_graph
+        self._side = torch.cuda.Stream(device=dev)      # weight-gradient work overlaps the data-gradient chain
         self._graph = None
         self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
 
@@ -110,6 +111,14 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ one forward + loss + backward (no optimiser)
     def _fwd_bwd(self):
+        K.SIDE.stream = self._side
+        try:
+            self._fwd_bwd_body()
+            K.join_side()
+        finally:
+            K.SIDE.stream = None
+
+    def _fwd_bwd_body(self):
         blk = self._blocks
         Pd, Gd = blk["ds"]
         emb, s_ds = K.deepsets_fwd(Pd, self.ens)

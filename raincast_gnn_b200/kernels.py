@@ -10,6 +10,7 @@ torch.nn.BatchNorm1d / Linear; see include/rc_b200.h for the per-kernel citation
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 
@@ -26,6 +27,41 @@ _SM = 148
 
 def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _Side:
+    """Optional second stream for work that is off the critical path of backward (weight / bias gradients and
+    their reductions).  Enabled by the graphed engine: inside a CUDA-graph capture the event waits become graph
+    edges, so the weight-gradient GEMMs run concurrently with the data-gradient chain on otherwise idle SMs."""
+    stream = None
+    keep: list = []
+
+
+SIDE = _Side()
+
+
+@contextlib.contextmanager
+def on_side(*inputs):
+    """Run the enclosed launches on the side stream, ordered after everything issued so far on the current stream.
+    `inputs` (tensors produced on the main stream and read here) are kept alive until join_side()."""
+    if SIDE.stream is None:
+        yield
+        return
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    SIDE.stream.wait_event(ev)
+    SIDE.keep.extend(inputs)
+    with torch.cuda.stream(SIDE.stream):
+        yield
+
+
+def join_side():
+    if SIDE.stream is None:
+        return
+    ev = torch.cuda.Event()
+    ev.record(SIDE.stream)
+    torch.cuda.current_stream().wait_event(ev)
+    SIDE.keep.clear()
 
 
 def operand(t, ld, op=RC_OP_NONE, p=(None, None, None, None), aux=None, ld_aux=0, bits=None, ld_bits=0):
@@ -151,13 +187,16 @@ def deepsets_bwd(P, saved, d_emb, G):
     sink = GradSink(dev)
     ho = P["rho2_w"].shape[0]
     # rho[2]
-    linear_bwd_weight(operand(d_emb, ho), operand(r1, h), m, ho, h, G["rho2_w"], G["rho2_b"], sink)
+    with on_side(d_emb):
+        linear_bwd_weight(operand(d_emb, ho), operand(r1, h), m, ho, h, G["rho2_w"], G["rho2_b"], sink)
     d_r1 = linear_bwd_data(d_emb, P["rho2_w"], mask_pos=r1)
     # rho[0]
-    linear_bwd_weight(operand(d_r1, h), operand(s2, h), m, h, h, G["rho0_w"], G["rho0_b"], sink)
+    with on_side(d_r1):
+        linear_bwd_weight(operand(d_r1, h), operand(s2, h), m, h, h, G["rho0_w"], G["rho0_b"], sink)
     d_s2 = linear_bwd_data(d_r1, P["rho0_w"])
     # phi[2] (after the pool): bias gradient carries the member count
-    linear_bwd_weight(operand(d_s2, h), operand(pooled, h), m, h, h, G["phi2_w"], G["phi2_b"], sink, bias_scale=float(em))
+    with on_side(d_s2):
+        linear_bwd_weight(operand(d_s2, h), operand(pooled, h), m, h, h, G["phi2_w"], G["phi2_b"], sink, bias_scale=float(em))
     d_pooled = linear_bwd_data(d_s2, P["phi2_w"])
     # phi[0] + ReLU, per member
     nb = int(L.rc_deepsets_pool_bwd_nblocks(m, h))
@@ -166,7 +205,8 @@ def deepsets_bwd(P, saved, d_emb, G):
                                       part.data_ptr(), m, em, f, h, _stream(ens)), "rc_deepsets_pool_bwd")
     sink.add(part, G["phi0_w"], h * f + h, nb, h * f)
     sink.add(part.reshape(-1)[h * f:], G["phi0_b"], h * f + h, nb, h)
-    sink.flush()
+    with on_side(part):
+        sink.flush()
 
 
 # --------------------------------------------------------------------------------------------- dim_red
@@ -190,9 +230,10 @@ def dimred_bwd(P, saved, dy, G):
     n, ldw = w.shape
     sink = GradSink(x.device)
     dw = G["dimred_w"]
-    linear_bwd_weight(operand(dy, n), operand(x, f), m, n, f, dw[:, :f], G["dimred_b"], sink, dw_ld=ldw)
-    linear_bwd_weight(operand(dy, n), operand(emb, h_in), m, n, h_in, dw[:, f:], None, sink, dw_ld=ldw)
-    sink.flush()
+    with on_side(dy):
+        linear_bwd_weight(operand(dy, n), operand(x, f), m, n, f, dw[:, :f], G["dimred_b"], sink, dw_ld=ldw)
+        linear_bwd_weight(operand(dy, n), operand(emb, h_in), m, n, h_in, dw[:, f:], None, sink, dw_ld=ldw)
+        sink.flush()
     return linear_bwd_data(dy, w, w_ld=ldw, w_col0=f, k=h_in)
 
 
@@ -248,8 +289,9 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     sink = GradSink(dev)
     do_op = operand(dy, out_dim, RC_OP_BITMASK, bits=bits, ld_bits=words)           # d o = dy * 1[o > 0]
     # Linear2: d W2 = d o^T u,  u = relu(BN(t)) recomputed in the prologue
-    linear_bwd_weight(do_op, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), m, out_dim, hid,
-                      G["nn3_w"], G["nn3_b"], sink)
+    with on_side(dy):
+        linear_bwd_weight(do_op, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), m, out_dim, hid,
+                          G["nn3_w"], G["nn3_b"], sink)
     # d z = (d o @ W2) * 1[BN(t) > 0], with the two BatchNorm column reductions in the epilogue
     row_tile = gemm_row_tile(m, hid)
     tiles = math.ceil(m / row_tile)
@@ -264,8 +306,9 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
                                     G["bn_w"].data_ptr(), G["bn_b"].data_ptr(), c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), st),
                "rc_bn_bwd_finalize")
     dt_op = operand(dz, hid, RC_OP_AFFINE2, (c0, c1, c2, mean), aux=t, ld_aux=hid)  # d t = c0*dz + c1*(t-mean) + c2
-    linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
-    sink.flush()
+    with on_side(dz, c0, c1, c2):
+        linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
+        sink.flush()
     d_agg = torch.empty((m, h), dtype=torch.float32, device=dev)
     gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
     # aggregation backward (+ residual branch of layers > 0)
@@ -275,8 +318,9 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     _lib.check(L.rc_gine_aggr_bwd(d_agg.data_ptr(), x.data_ptr(), graph.t_rowptr.data_ptr(), graph.t_dst.data_ptr(),
                                   graph.t_attr.data_ptr(), P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(),
                                   None if first else dy.data_ptr(), dx.data_ptr(), part.data_ptr(), m, h, st), "rc_gine_aggr_bwd")
-    _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, G["lin_w"].data_ptr(), G["lin_b"].data_ptr(),
-                                           G["eps"].data_ptr(), st), "rc_gine_aggr_bwd_finalize")
+    with on_side(part, d_agg):
+        _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, G["lin_w"].data_ptr(), G["lin_b"].data_ptr(),
+                                               G["eps"].data_ptr(), _stream(x)), "rc_gine_aggr_bwd_finalize")
     return dx if need_dx else None
 
 
@@ -290,8 +334,9 @@ def head_bwd(P, saved, d_raw, G):
     m, h = x.shape
     c = P["aggr_w"].shape[0]
     sink = GradSink(x.device)
-    linear_bwd_weight(operand(d_raw, c), operand(x, h), m, c, h, G["aggr_w"], G["aggr_b"], sink)
-    sink.flush()
+    with on_side(d_raw):
+        linear_bwd_weight(operand(d_raw, c), operand(x, h), m, c, h, G["aggr_w"], G["aggr_b"], sink)
+        sink.flush()
     return linear_bwd_data(d_raw, P["aggr_w"])
 
 

@@ -340,3 +340,43 @@ def test_adamw_kernel_matches_torch(dev):
     assert rel_err(_np(p), ref.detach().numpy()) < 1e-6
     # the update itself (~5e-4 on parameters of size ~1): limited by fp32 rounding of p, not by the kernel
     assert rel_err(_np(p - p0.to(dev)), (ref.detach() - p0).numpy()) < 2e-3
+
+
+@pytest.mark.parametrize("h", [128, 256])
+def test_gine_aggregation_large_graph_path(dev, h):
+    """The contiguous-range kernels used from 16 384 rows up, on a 20k-node radius graph.  54 M ReLU units: inputs
+    are dyadic rationals so that every pre-activation x_j + a*w + b is exact in fp32 and float64 alike and no unit
+    sits within rounding of its threshold (the comparison then tests the kernel, not the conditioning)."""
+    from raincast_gnn_b200 import _lib, graph as G
+    from raincast_gnn_b200.utils import synthetic as syn
+    m = 20_000
+    coords = syn.station_coords(m, 450.0, seed=2)
+    ei, _ = G.radius_graph_from_coords(coords, syn.scaled_graph_radius(m, 450.0, 20.0))
+    g = torch.Generator().manual_seed(h)
+
+    def dyadic(*shape, scale=8.0):
+        return torch.round(torch.randn(*shape, generator=g, dtype=torch.float64) * scale) / scale
+    ea = (torch.randint(1, 64, (ei.shape[1], 1), generator=g).double() / 4.0)
+    x, w, b = dyadic(m, h).requires_grad_(True), dyadic(h).requires_grad_(True), dyadic(h).requires_grad_(True)
+    eps = torch.tensor([-0.25], dtype=torch.float64, requires_grad=True)
+    gout = torch.randn(m, h, generator=g, dtype=torch.float64)
+    want = _gine_ref(x, ei, ea, w, b, eps)
+    want.backward(gout)
+    sg = G.build_station_graph(ei, ea.float(), m).to(dev)
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    xd, wd, bd, ed, gd = (t.detach().float().to(dev) for t in (x, w, b, eps, gout))
+    hh = torch.empty(m, h, device=dev)
+    _lib.check(L.rc_gine_aggr_fwd(xd.data_ptr(), sg.rowptr.data_ptr(), sg.col.data_ptr(), sg.attr.data_ptr(), wd.data_ptr(),
+                                  bd.data_ptr(), ed.data_ptr(), hh.data_ptr(), m, h, st))
+    assert rel_err(_np(hh), want.detach().numpy()) < TOL
+    nb = L.rc_gine_aggr_bwd_nblocks(m, h)
+    part = torch.empty(nb, 3, h, device=dev)
+    dx = torch.empty(m, h, device=dev)
+    _lib.check(L.rc_gine_aggr_bwd(gd.data_ptr(), xd.data_ptr(), sg.t_rowptr.data_ptr(), sg.t_dst.data_ptr(), sg.t_attr.data_ptr(),
+                                  wd.data_ptr(), bd.data_ptr(), ed.data_ptr(), None, dx.data_ptr(), part.data_ptr(), m, h, st))
+    dw, db, de = torch.empty(h, device=dev), torch.empty(h, device=dev), torch.empty(1, device=dev)
+    _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, dw.data_ptr(), db.data_ptr(), de.data_ptr(), st))
+    assert rel_err(_np(dx), x.grad.numpy()) < TOL
+    assert rel_err(_np(dw), w.grad.numpy()) < TOL and rel_err(_np(db), b.grad.numpy()) < TOL
+    assert rel_err(_np(de), eps.grad.numpy()) < TOL
