@@ -1,0 +1,241 @@
+// BatchNorm finalisers, segmented reduction and AdamW tile functions shared by rc_misc.cu and rc_prog.cu.
+#pragma once
+#include "rc_common.cuh"
+
+namespace rc {
+
+struct BnStatsFinP {
+  const float* stats;
+  int row_tiles;
+  int row_tile;
+  int m;
+  int n;
+  float eps;
+  float momentum;
+  float* mean_out;
+  float* rstd_out;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+};
+
+struct BnEvalP {
+  const float* running_mean;
+  const float* running_var;
+  int n;
+  float eps;
+  float* mean;
+  float* rstd;
+};
+
+struct BnBwdFinP {
+  const float* stats;
+  int row_tiles;
+  int m;
+  int n;
+  int batch_stats;
+  const float* gamma;
+  const float* mean;
+  const float* rstd;
+  float* d_gamma;
+  float* d_beta;
+  float* c0;
+  float* c1;
+  float* c2;
+};
+
+struct AdamTickP {
+  long long* step;
+};
+
+struct AdamP {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  const long long* step;
+  long long n;
+  float lr;
+  float beta1;
+  float beta2;
+  float eps;
+  float weight_decay;
+  float grad_scale;
+};
+
+
+
+// ---------------------------------------------------------------------------- BatchNorm forward stats
+// block (32 columns, 8 tile strides); Chan's pairwise update in float64, merged in a fixed order.
+struct Moments { double n, mean, m2; };
+__device__ __forceinline__ void chan_merge(Moments& a, double nb, double mean_b, double m2_b) {
+  if (nb <= 0.0) return;
+  const double n = a.n + nb, delta = mean_b - a.mean;
+  a.mean += delta * (nb / n);
+  a.m2 += m2_b + delta * delta * (a.n * nb / n);
+  a.n = n;
+}
+
+__device__ __forceinline__ void bn_stats_fin_tile(const BnStatsFinP& p, const uint3 bid, const uint3 gdim) {
+  const float* __restrict__ stats = p.stats;
+  int row_tiles = p.row_tiles;
+  int row_tile = p.row_tile;
+  int m = p.m;
+  int n = p.n;
+  float eps = p.eps;
+  float momentum = p.momentum;
+  float* mean_out = p.mean_out;
+  float* rstd_out = p.rstd_out;
+  float* running_mean = p.running_mean;
+  float* running_var = p.running_var;
+  long long* num_batches_tracked = p.num_batches_tracked;
+  (void)bid; (void)gdim;
+
+  __shared__ double sh[8][3][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = bid.x * 32 + tx;
+  Moments acc = {0.0, 0.0, 0.0};
+  if (col < n)
+    for (int t = ty; t < row_tiles; t += 8) {
+      const int cnt = min(row_tile, m - t * row_tile);
+      chan_merge(acc, (double)cnt, (double)stats[(size_t)t * 2 * n + col], (double)stats[(size_t)t * 2 * n + n + col]);
+    }
+  sh[ty][0][tx] = acc.n; sh[ty][1][tx] = acc.mean; sh[ty][2][tx] = acc.m2;
+  __syncthreads();
+  if (ty == 0 && col < n) {
+    Moments tot = {0.0, 0.0, 0.0};
+    for (int k = 0; k < 8; ++k) chan_merge(tot, sh[k][0][tx], sh[k][1][tx], sh[k][2][tx]);
+    const double var_b = tot.m2 / (double)m;
+    mean_out[col] = (float)tot.mean;
+    rstd_out[col] = (float)(1.0 / sqrt(var_b + (double)eps));
+    if (running_mean != nullptr) running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)tot.mean;
+    if (running_var != nullptr) {
+      const float var_u = (float)(tot.m2 / (double)(m > 1 ? m - 1 : 1));
+      running_var[col] = (1.0f - momentum) * running_var[col] + momentum * var_u;
+    }
+  }
+  if (bid.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) num_batches_tracked[0] += 1;
+}
+
+__device__ __forceinline__ void bn_eval_tile(const BnEvalP& p, const uint3 bid, const uint3 gdim) {
+  const float* __restrict__ running_mean = p.running_mean;
+  const float* __restrict__ running_var = p.running_var;
+  int n = p.n;
+  float eps = p.eps;
+  float* mean = p.mean;
+  float* rstd = p.rstd;
+  (void)bid; (void)gdim;
+
+  const int i = bid.x * 256 + threadIdx.x;
+  if (i < n) {
+    mean[i] = running_mean[i];
+    rstd[i] = 1.0f / sqrtf(running_var[i] + eps);
+  }
+}
+
+// ---------------------------------------------------------------------------- BatchNorm backward coefficients
+__device__ __forceinline__ void bn_bwd_fin_tile(const BnBwdFinP& p, const uint3 bid, const uint3 gdim) {
+  const float* __restrict__ stats = p.stats;
+  int row_tiles = p.row_tiles;
+  int m = p.m;
+  int n = p.n;
+  int batch_stats = p.batch_stats;
+  const float* __restrict__ gamma = p.gamma;
+  const float* __restrict__ mean = p.mean;
+  const float* __restrict__ rstd = p.rstd;
+  float* d_gamma = p.d_gamma;
+  float* d_beta = p.d_beta;
+  float* c0 = p.c0;
+  float* c1 = p.c1;
+  float* c2 = p.c2;
+  (void)bid; (void)gdim;
+
+  __shared__ double sh[8][2][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = bid.x * 32 + tx;
+  double s0 = 0.0, s1 = 0.0;
+  if (col < n)
+    for (int t = ty; t < row_tiles; t += 8) {
+      s0 += (double)stats[(size_t)t * 2 * n + col];
+      s1 += (double)stats[(size_t)t * 2 * n + n + col];
+    }
+  sh[ty][0][tx] = s0; sh[ty][1][tx] = s1;
+  __syncthreads();
+  if (ty == 0 && col < n) {
+    double db = 0.0, dg = 0.0;
+    for (int k = 0; k < 8; ++k) { db += sh[k][0][tx]; dg += sh[k][1][tx]; }
+    d_beta[col] = (float)db;
+    d_gamma[col] = (float)dg;
+    // d t = gamma*rstd * (dz - d_beta/M - xhat * d_gamma/M),  xhat = (t - mean) * rstd
+    const double gr = (double)gamma[col] * (double)rstd[col];
+    c0[col] = (float)gr;
+    // (eval mode, running statistics: the mean/variance are constants and only c0 survives)
+    c1[col] = batch_stats ? (float)(-gr * (double)rstd[col] * dg / (double)m) : 0.f;
+    c2[col] = batch_stats ? (float)(-gr * db / (double)m) : 0.f;
+    (void)mean;
+  }
+}
+
+// ---------------------------------------------------------------------------- segmented partial reduction
+struct ReduceArgs { rc_reduce_seg seg[RC_REDUCE_MAX_SEGS]; };
+using ReduceP = ReduceArgs;
+__device__ __forceinline__ void reduce_tile(const ReduceP& p, const uint3 bid, const uint3 gdim) {
+  const ReduceArgs& args = p;
+  (void)bid; (void)gdim;
+
+  const rc_reduce_seg& sg = args.seg[bid.y];
+  for (int j = bid.x * 256 + threadIdx.x; j < sg.n; j += gdim.x * 256) {
+    double s = 0.0;
+    for (int p = 0; p < sg.parts; ++p) s += (double)__ldg(sg.src + (size_t)p * sg.stride + j);
+    const float v = sg.scale * (float)s;
+    float* out = sg.dst + (sg.row_len > 0 ? (size_t)(j / sg.row_len) * sg.dst_ld + (j % sg.row_len) : (size_t)j);
+    *out = sg.accumulate ? *out + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------- AdamW
+// torch.optim.AdamW single-tensor update (decoupled weight decay, bias-corrected moments).
+__device__ __forceinline__ void adamw_tick_tile(const AdamTickP& p, const uint3 bid, const uint3 gdim) {
+  long long* step = p.step;
+  (void)bid; (void)gdim;
+  if (threadIdx.x == 0) step[0] += 1;
+}
+
+__device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, const uint3 gdim) {
+  float* __restrict__ param = p.param;
+  const float* __restrict__ grad = p.grad;
+  float* __restrict__ exp_avg = p.exp_avg;
+  float* __restrict__ exp_avg_sq = p.exp_avg_sq;
+  const long long* __restrict__ step = p.step;
+  long long n = p.n;
+  float lr = p.lr;
+  float beta1 = p.beta1;
+  float beta2 = p.beta2;
+  float eps = p.eps;
+  float weight_decay = p.weight_decay;
+  float grad_scale = p.grad_scale;
+  (void)bid; (void)gdim;
+
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = (double)step[0];
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    s_step_size = (float)((double)lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  for (long long i = (long long)bid.x * 256 + threadIdx.x; i < n; i += (long long)gdim.x * 256) {
+    const float g = grad[i] * grad_scale;
+    float p = param[i] * (1.0f - lr * weight_decay);
+    float m1 = exp_avg[i], v = exp_avg_sq[i];
+    m1 = m1 + (g - m1) * (1.0f - beta1);                 // lerp_
+    v = v * beta2 + (1.0f - beta2) * g * g;              // mul_ + addcmul_
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p = p - step_size * (m1 / denom);
+    param[i] = p; exp_avg[i] = m1; exp_avg_sq[i] = v;
+  }
+}
+
+
+}  // namespace rc

@@ -40,10 +40,38 @@ class _Side:
 SIDE = _Side()
 
 
+class _Record:
+    """Step-program recording (rc_prog_*): while active, library calls append to a program instead of launching,
+    so every tensor they name must outlive the program — `keep` holds all buffers allocated here meanwhile."""
+    active = False
+    keep: list = []
+
+
+RECORD = _Record()
+
+
+def _new(shape, dtype=torch.float32, device=None):
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if RECORD.active:
+        RECORD.keep.append(t)
+    return t
+
+
+def _new_like(ref):
+    return _new(ref.shape, ref.dtype, ref.device)
+
+
 @contextlib.contextmanager
 def on_side(*inputs):
     """Run the enclosed launches on the side stream, ordered after everything issued so far on the current stream.
     `inputs` (tensors produced on the main stream and read here) are kept alive until join_side()."""
+    if RECORD.active:                      # step program: lane 1 = off the critical path
+        _lib.check(_lib.lib().rc_prog_lane(1), "rc_prog_lane")
+        try:
+            yield
+        finally:
+            _lib.check(_lib.lib().rc_prog_lane(0), "rc_prog_lane")
+        return
     if SIDE.stream is None:
         yield
         return
@@ -56,6 +84,9 @@ def on_side(*inputs):
 
 
 def join_side():
+    if RECORD.active:
+        _lib.check(_lib.lib().rc_prog_join(), "rc_prog_join")
+        return
     if SIDE.stream is None:
         return
     ev = torch.cuda.Event()
@@ -93,7 +124,7 @@ def linear_fwd(x, w, b, *, relu=False, bias_scale=1.0):
     """y = [relu](x @ w^T + bias_scale*b);  x [M,K], w [N,K]."""
     m, k = x.shape
     n = w.shape[0]
-    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    y = _new((m, n), torch.float32, x.device)
     gemm(m, n, k, operand(x, k), operand(w, k), y, n, bias=b, bias_scale=bias_scale,
          epi=RC_EPI_RELU if relu else RC_EPI_NONE)
     return y
@@ -104,7 +135,7 @@ def linear_bwd_data(dy, w, *, mask_pos=None, w_ld=None, w_col0=0, k=None):
     m, n = dy.shape
     w_ld = w.shape[1] if w_ld is None else w_ld
     k = w.shape[1] - w_col0 if k is None else k
-    dx = torch.empty((m, k), dtype=torch.float32, device=dy.device)
+    dx = _new((m, k), torch.float32, dy.device)
     wv = w if w_col0 == 0 else w.reshape(-1)[w_col0:]
     gemm(m, k, n, operand(dy, n), operand(wv, w_ld), dx, k, b_layout=RC_B_RED,
          epi=RC_EPI_MASK_POS if mask_pos is not None else RC_EPI_NONE, e_aux=mask_pos, ld_e_aux=k)
@@ -151,8 +182,8 @@ def linear_bwd_weight(dy_op: _lib.rc_operand, x_op: _lib.rc_operand, m, n, k, dw
     if direct:
         gemm(n, k, m, dy_op, x_op, dw, k, a_layout=RC_A_RED, b_layout=RC_B_RED, colsum_a=db)
         return
-    part = torch.empty((splits, n, k), dtype=torch.float32, device=dev)
-    cs = torch.empty((splits, n), dtype=torch.float32, device=dev) if db is not None else None
+    part = _new((splits, n, k), torch.float32, dev)
+    cs = _new((splits, n), torch.float32, dev) if db is not None else None
     gemm(n, k, m, dy_op, x_op, part, k, a_layout=RC_A_RED, b_layout=RC_B_RED, splits=splits, split_stride=n * k,
          colsum_a=cs)
     if dw_ld == k:
@@ -169,7 +200,7 @@ def deepsets_fwd(P, ens):
     m, em, f = ens.shape
     h = P["phi0_w"].shape[0]
     L = _lib.lib()
-    pooled = torch.empty((m, h), dtype=torch.float32, device=ens.device)
+    pooled = _new((m, h), torch.float32, ens.device)
     _lib.check(L.rc_deepsets_pool_fwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), pooled.data_ptr(),
                                       m, em, f, h, _stream(ens)), "rc_deepsets_pool_fwd")
     s2 = linear_fwd(pooled, P["phi2_w"], P["phi2_b"], bias_scale=float(em))       # sum_e (h_e W^T + b)
@@ -200,7 +231,7 @@ def deepsets_bwd(P, saved, d_emb, G):
     d_pooled = linear_bwd_data(d_s2, P["phi2_w"])
     # phi[0] + ReLU, per member
     nb = int(L.rc_deepsets_pool_bwd_nblocks(m, h))
-    part = torch.empty((nb, h * f + h), dtype=torch.float32, device=dev)
+    part = _new((nb, h * f + h), torch.float32, dev)
     _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), d_pooled.data_ptr(),
                                       part.data_ptr(), m, em, f, h, _stream(ens)), "rc_deepsets_pool_bwd")
     sink.add(part, G["phi0_w"], h * f + h, nb, h * f)
@@ -216,7 +247,7 @@ def dimred_fwd(P, x, emb):
     h_in = emb.shape[1]
     w = P["dimred_w"]
     n, ldw = w.shape
-    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    y = _new((m, n), torch.float32, x.device)
     gemm(m, n, f, operand(x, f), operand(w, ldw), y, n, bias=P["dimred_b"],
          a2=emb, lda2=h_in, b2=w.reshape(-1)[f:], ldb2=ldw, k2=h_in)
     return y, (x, emb)
@@ -245,20 +276,20 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     m, h = x.shape
     dev = x.device
     st = _stream(x)
-    agg = torch.empty_like(x)
+    agg = _new_like(x)
     _lib.check(L.rc_gine_aggr_fwd(x.data_ptr(), graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.attr.data_ptr(),
                                   P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(), agg.data_ptr(),
                                   m, h, st), "rc_gine_aggr_fwd")
     hid = P["nn0_w"].shape[0]
-    t = torch.empty((m, hid), dtype=torch.float32, device=dev)
-    mean = torch.empty(hid, dtype=torch.float32, device=dev)
-    rstd = torch.empty(hid, dtype=torch.float32, device=dev)
+    t = _new((m, hid), torch.float32, dev)
+    mean = _new(hid, torch.float32, dev)
+    rstd = _new(hid, torch.float32, dev)
     if training:
         if m < 2:
             raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d)")
         row_tile = gemm_row_tile(m, hid)
         tiles = math.ceil(m / row_tile)
-        stats = torch.empty((tiles, 2, hid), dtype=torch.float32, device=dev)
+        stats = _new((tiles, 2, hid), torch.float32, dev)
         gemm(m, hid, h, operand(agg, h), operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"], epi=RC_EPI_BN_STATS, stats=stats)
         _lib.check(L.rc_bn_stats_finalize(stats.data_ptr(), tiles, row_tile, m, hid, BN_EPS, BN_MOMENTUM, mean.data_ptr(),
                                           rstd.data_ptr(), P["bn_rm"].data_ptr(), P["bn_rv"].data_ptr(),
@@ -268,9 +299,9 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
         _lib.check(L.rc_bn_eval_prepare(P["bn_rm"].data_ptr(), P["bn_rv"].data_ptr(), hid, BN_EPS, mean.data_ptr(),
                                         rstd.data_ptr(), st), "rc_bn_eval_prepare")
     out_dim = P["nn3_w"].shape[0]
-    y = torch.empty((m, out_dim), dtype=torch.float32, device=dev)
+    y = _new((m, out_dim), torch.float32, dev)
     words = math.ceil(out_dim / 32)
-    bits = torch.empty((m, words), dtype=torch.int32, device=dev)
+    bits = _new((m, words), torch.int32, dev)
     gemm(m, out_dim, hid, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), operand(P["nn3_w"], hid),
          y, out_dim, bias=P["nn3_b"], epi=RC_EPI_RELU if first else RC_EPI_RELU_RES, res=None if first else x,
          ld_res=h, bits_out=bits, ld_bits_out=words)
@@ -295,13 +326,13 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     # d z = (d o @ W2) * 1[BN(t) > 0], with the two BatchNorm column reductions in the epilogue
     row_tile = gemm_row_tile(m, hid)
     tiles = math.ceil(m / row_tile)
-    stats = torch.empty((tiles, 2, hid), dtype=torch.float32, device=dev)
-    dz = torch.empty((m, hid), dtype=torch.float32, device=dev)
+    stats = _new((tiles, 2, hid), torch.float32, dev)
+    dz = _new((m, hid), torch.float32, dev)
     gemm(m, hid, out_dim, do_op, operand(P["nn3_w"], hid), dz, hid, b_layout=RC_B_RED, epi=RC_EPI_BN_RELU_BWD, e_aux=t,
          ld_e_aux=hid, e_p=(mean, rstd, P["bn_w"], P["bn_b"]), stats=stats)
-    c0 = torch.empty(hid, dtype=torch.float32, device=dev)
-    c1 = torch.empty_like(c0)
-    c2 = torch.empty_like(c0)
+    c0 = _new(hid, torch.float32, dev)
+    c1 = _new_like(c0)
+    c2 = _new_like(c0)
     _lib.check(L.rc_bn_bwd_finalize(stats.data_ptr(), tiles, m, hid, int(training), P["bn_w"].data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                     G["bn_w"].data_ptr(), G["bn_b"].data_ptr(), c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), st),
                "rc_bn_bwd_finalize")
@@ -309,12 +340,12 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     with on_side(dz, c0, c1, c2):
         linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
         sink.flush()
-    d_agg = torch.empty((m, h), dtype=torch.float32, device=dev)
+    d_agg = _new((m, h), torch.float32, dev)
     gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
     # aggregation backward (+ residual branch of layers > 0)
     nb = int(L.rc_gine_aggr_bwd_nblocks(m, h))
-    part = torch.empty((nb, 3, h), dtype=torch.float32, device=dev)
-    dx = torch.empty((m, h), dtype=torch.float32, device=dev)
+    part = _new((nb, 3, h), torch.float32, dev)
+    dx = _new((m, h), torch.float32, dev)
     _lib.check(L.rc_gine_aggr_bwd(d_agg.data_ptr(), x.data_ptr(), graph.t_rowptr.data_ptr(), graph.t_dst.data_ptr(),
                                   graph.t_attr.data_ptr(), P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(),
                                   None if first else dy.data_ptr(), dx.data_ptr(), part.data_ptr(), m, h, st), "rc_gine_aggr_bwd")
@@ -342,28 +373,28 @@ def head_bwd(P, saved, d_raw, G):
 
 # --------------------------------------------------------------------------------------------- links + CRPS
 def postprocess_fwd(raw, kind):
-    post = torch.empty_like(raw)
+    post = _new_like(raw)
     _lib.check(_lib.lib().rc_postprocess_fwd(raw.data_ptr(), post.data_ptr(), raw.shape[0], kind, _stream(raw)), "rc_postprocess_fwd")
     return post
 
 
 def postprocess_bwd(raw, d_post, kind):
-    d_raw = torch.empty_like(raw)
+    d_raw = _new_like(raw)
     _lib.check(_lib.lib().rc_postprocess_bwd(raw.data_ptr(), d_post.data_ptr(), d_raw.data_ptr(), raw.shape[0], kind, _stream(raw)),
                "rc_postprocess_bwd")
     return d_raw
 
 
-def crps_fwd_bwd(pred, y, kind, *, raw_input=False, u=0.0, xi=0.5, t=5.0, need_grad=True):
+def crps_fwd_bwd(pred, y, kind, *, raw_input=False, u=0.0, xi=0.5, t=5.0, need_grad=True, loss_out=None):
     """(loss float64 [1], d_pred or None, n_valid int32 [1]); d_pred already carries the 1/n_valid of the mean."""
     L = _lib.lib()
     m = pred.shape[0]
     dev = pred.device
     ws_bytes = int(L.rc_crps_workspace(m))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    loss = torch.empty(1, dtype=torch.float64, device=dev)
-    n_valid = torch.empty(1, dtype=torch.int32, device=dev)
-    d_pred = torch.empty_like(pred) if need_grad else None
+    ws = _new(ws_bytes, torch.uint8, dev)
+    loss = loss_out if loss_out is not None else _new(1, torch.float64, dev)
+    n_valid = _new(1, torch.int32, dev)
+    d_pred = _new_like(pred) if need_grad else None
     _lib.check(L.rc_crps_fwd_bwd(pred.data_ptr(), y.data_ptr(), _lib.ptr(d_pred), loss.data_ptr(), n_valid.data_ptr(), m, kind,
                                  int(raw_input), float(u), float(xi), float(t), ws.data_ptr(), ws_bytes, _stream(pred)),
                "rc_crps_fwd_bwd")

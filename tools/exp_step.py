@@ -14,10 +14,12 @@ ei, ea, ei_b, ea_b = B.static_graph(bsz)
 m = bsz * B.N_STATIONS
 sg = build_station_graph(ei_b, ea_b, m).to(dev)
 model = B.seeded_model(GNN).to(dev).train()
-eng = TrainEngine(model, sg, m, B.MEMBERS, B.FEATS).capture()
+eng = TrainEngine(model, sg, m, B.MEMBERS, B.FEATS, mode="graph").capture()
+engp = TrainEngine(B.seeded_model(GNN).to(dev).train(), sg, m, B.MEMBERS, B.FEATS, mode="program").capture()
 from raincast_gnn_b200.utils import synthetic as syn
 x, ens = syn.node_features(m, B.MEMBERS, B.FEATS, seed=1); y = syn.log_precip_targets(m, seed=1)
 eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
+engp.load_batch(x.to(dev), ens.to(dev), y.to(dev))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def timeit(fn, n=100, do_flush=False):
@@ -41,8 +43,11 @@ print(f"step, L2 flushed      : {timeit(eng.step, do_flush=True):8.1f} us")
 print(f"step, back to back    : {timeit(eng.step):8.1f} us")
 print(f"graph replay only     : {timeit(eng._graph.replay):8.1f} us")
 print(f"optimizer only        : {timeit(eng._optimizer):8.1f} us")
+print(f"program: ops {engp.prog_ops} phases {engp.prog_phases}")
+print(f"program step, flushed : {timeit(engp.step, do_flush=True):8.1f} us")
+print(f"program step, b2b     : {timeit(engp.step):8.1f} us")
 # eager (no graph) for comparison
-eng2 = TrainEngine(B.seeded_model(GNN).to(dev).train(), sg, m, B.MEMBERS, B.FEATS, use_cuda_graph=False).capture()
+eng2 = TrainEngine(B.seeded_model(GNN).to(dev).train(), sg, m, B.MEMBERS, B.FEATS, use_cuda_graph=False, mode="graph").capture()
 eng2.load_batch(x.to(dev), ens.to(dev), y.to(dev))
 print(f"eager step (no graph) : {timeit(eng2.step, n=30):8.1f} us")
 # forward only pieces, eager timing of individual blocks back to back (warm L2)
@@ -63,3 +68,13 @@ with torch.cuda.stream(s):
     with torch.cuda.graph(g):
         for _ in range(74): z.add_(1)
 print(f"74 chained tiny nodes : {timeit(g.replay):8.1f} us")
+
+# grid barrier cost: a program of 50 empty phases
+import ctypes as C
+L = _lib.lib()
+L.rc_prog_begin()
+for _ in range(50): L.rc_prog_nop()
+nb = L.rc_prog_bytes(); buf = torch.empty(nb, dtype=torch.uint8, device=dev); info = (C.c_int * 4)()
+_lib.check(L.rc_prog_end(buf.data_ptr(), nb, info))
+st = torch.cuda.current_stream().cuda_stream
+print(f"50 empty phases       : {timeit(lambda: L.rc_prog_run(buf.data_ptr(), info, st)):8.1f} us")
