@@ -190,6 +190,11 @@ int rc_reduce_segments(const rc_reduce_seg* segs, int n_segs, void* stream);
  *  over members commutes with it exactly in real arithmetic). */
 int rc_deepsets_pool_fwd(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
                          int members, int feats, int hidden, void* stream);
+/* Same contraction with bf16 operands and fp32 accumulation on the tensor cores (tcgen05 + TMEM; BASELINE.json
+ * config 5).  rc_deepsets_pool_fwd itself switches to the tensor cores with an fp32-accurate 3xTF32 split when
+ * num_nodes*members >= 65536 and 128 | hidden (override: RC_DEEPSETS_TC=0/1). */
+int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
+                              int members, int feats, int hidden, void* stream);
 /* d w1 / d b1 partials from d pooled (ReLU mask recomputed, nothing saved in forward):
  * partials[nblocks][H*F + H]. */
 int rc_deepsets_pool_bwd_nblocks(int num_nodes, int hidden);

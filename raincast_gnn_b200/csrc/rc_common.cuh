@@ -56,4 +56,9 @@ int launch_gine_bwd_ranged(const float* g, const float* x, const int* t_rowptr, 
                            const float* w_edge, const float* b_edge, const float* eps, const float* addend, float* dx,
                            float* partials, int m, int hidden, cudaStream_t s);
 
+// rc_deepsets_tc.cu: tcgen05 / TMEM path of the DeepSets member Linear + ReLU + pool
+bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden);
+int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
+                           int members, int feats, int hidden, cudaStream_t s);
+
 }  // namespace rc

@@ -30,6 +30,8 @@ extern "C" int rc_deepsets_pool_fwd(const float* ens, const float* w1, const flo
     return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd: bad argument");
   if (num_nodes == 0) return RC_OK;
   if (!aligned16(pooled) && hidden % 4 == 0) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd: pooled must be 16-byte aligned");
+  if (deepsets_tc_applicable(num_nodes, members, feats, hidden))      // large shapes: tensor cores, fp32-accurate 3xTF32
+    return launch_deepsets_fwd_tc(false, ens, w1, b1, pooled, num_nodes, members, feats, hidden, static_cast<cudaStream_t>(stream));
   const int f4 = (feats + 3) & ~3;
   const size_t smem = ((size_t)f4 * kDsCols + kDsCols + (size_t)kDsWarps * kDsMemberChunk * f4) * sizeof(float);
   if (smem > 200 * 1024) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd: feats=%d too large for the shared-memory tile", feats);
@@ -45,6 +47,16 @@ extern "C" int rc_deepsets_pool_fwd(const float* ens, const float* w1, const flo
   if (recording()) return record_op(OP_DS_FWD, 0, grid, smem, &p, sizeof(p));
   deepsets_pool_fwd_kernel<<<grid, kDsThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("deepsets_pool_fwd_kernel");
+}
+
+extern "C" int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
+                                         int members, int feats, int hidden, void* stream) {
+  if (!ens || !w1 || !b1 || !pooled || num_nodes < 0 || members <= 0 || feats <= 0 || hidden <= 0)
+    return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd_bf16: bad argument");
+  if (members > 128 || feats > 64) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd_bf16: needs members <= 128 and feats <= 64");
+  if (recording()) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd_bf16 cannot be recorded into a step program");
+  if (num_nodes == 0) return RC_OK;
+  return launch_deepsets_fwd_tc(true, ens, w1, b1, pooled, num_nodes, members, feats, hidden, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int rc_deepsets_pool_bwd_nblocks(int num_nodes, int hidden) {

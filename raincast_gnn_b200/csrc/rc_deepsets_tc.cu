@@ -1,0 +1,260 @@
+// DeepSets member Linear + ReLU + SUM pool on the 5th-generation tensor cores (tcgen05 + TMEM), for the shapes
+// where members x stations x hidden is a real dense contraction (BASELINE.json configs 4 and 5).
+//
+// The problem is transposed so that the pooling epilogue is free:   D[channel, member row] = W1 . E^T
+//   A = W1 tile      (M = 128 hidden channels, K = features)            shared memory, K-major, loaded once
+//   B = member rows  (N = 128 rows = whole stations, K = features)      shared memory, K-major, per tile
+//   D in TMEM: lane = channel, column = member row  ->  the thread that owns a lane sums ReLU(D + b1) over the
+//   columns of each station in registers and writes pooled[station, channel] (coalesced across the 128 lanes).
+// Nothing of size [M*members, H] exists anywhere (the reference materialises it twice, models/gnn.py:66-67).
+//
+// Precision: fp32 parity (1e-5) needs more than one TF32 product, so the fp32 mode issues the 3xTF32 split
+//   a = a_hi + a_lo (a_hi = cvt.rna.tf32), D += a_hi b_hi + a_hi b_lo + a_lo b_hi        (error ~2^-21 per product)
+// and the bf16 mode (config 5) one kind::f16 product with fp32 accumulation.
+// Operand tiles use the canonical no-swizzle K-major layout: 16-byte chunk c of row r at  c*2048 + r*16
+// (8 rows x 16 B core matrices; SBO = 128 B between 8-row groups, LBO = 2048 B between K-adjacent chunks).
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "rc_common.cuh"
+#include "rc_prog.h"
+
+namespace rc {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcRows = 128;          // MMA N: member rows per tile
+constexpr int kTcChunkBytes = kTcRows * 16;   // one 16-byte K chunk for 128 rows
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  // start address (>>4) | LBO (>>4) << 16 | SBO (>>4) << 32 | version 1 << 46 | SWIZZLE_NONE
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kTcChunkBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+         (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate));
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// dynamic shared memory (bytes), all 16-byte aligned:
+//   A_hi [chunks][128][16] | A_lo (fp32 mode) | B_hi | B_lo (fp32 mode) | staging [128*feats] fp32 | bias [128] | mbar | tmem ptr
+template <bool BF16>
+__global__ void __launch_bounds__(kTcThreads)
+deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restrict__ w1, const float* __restrict__ b1,
+                            float* __restrict__ pooled, int m, int members, int feats, int hidden, int nodes_per_tile,
+                            int chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kParts = BF16 ? 1 : 2;                 // hi (+ lo)
+  constexpr int kElemsPerChunk = BF16 ? 8 : 4;
+  const int op_bytes = chunks * kTcChunkBytes;
+  unsigned char* a_hi = smem_raw;
+  unsigned char* a_lo = a_hi + op_bytes;
+  unsigned char* b_hi = a_hi + kParts * op_bytes;
+  unsigned char* b_lo = b_hi + op_bytes;
+  float* staging = reinterpret_cast<float*>(b_hi + kParts * op_bytes);
+  float* bias = staging + kTcRows * feats;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(bias + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int c0 = blockIdx.y * 128;
+
+  // ---- one-time setup: TMEM (128 fp32 accumulator columns), mbarrier, W1 tile, bias
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  {
+    const int col = c0 + tid;                            // thread <-> hidden channel (row of the A tile)
+    bias[tid] = col < hidden ? __ldg(b1 + col) : 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < kElemsPerChunk; ++e) {
+        const int k = c * kElemsPerChunk + e;
+        v[e] = (col < hidden && k < feats) ? __ldg(w1 + (size_t)col * feats + k) : 0.f;
+      }
+      if (BF16) {
+        __nv_bfloat162 p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(a_hi + c * kTcChunkBytes + tid * 16) = *reinterpret_cast<uint4*>(p);
+      } else {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(v[e]); lo[e] = v[e] - hi[e]; }
+        *reinterpret_cast<float4*>(a_hi + c * kTcChunkBytes + tid * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a_lo + c * kTcChunkBytes + tid * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *tmem_slot;
+  const float my_bias = bias[tid];
+  // instruction descriptor: D fp32, A/B tf32 (2) or bf16 (1), both K-major, N = 128 (>>3), M = 128 (>>4)
+  const uint32_t fmt = BF16 ? 1u : 2u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTcRows >> 3) << 17) | ((128u >> 4) << 24);
+  const int ksteps = chunks / 2;                         // one MMA covers 32 bytes of K = 2 chunks
+  uint32_t phase = 0;
+
+  const int n_tiles = ceil_div(m, nodes_per_tile);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n0 = tile * nodes_per_tile;
+    const int n_nodes = min(nodes_per_tile, m - n0);
+    const int rows = n_nodes * members;
+    // ---- stage the tile's member rows (contiguous in HBM): coalesced 4-byte loads
+    const float* src = ens + (size_t)n0 * members * feats;
+    const int total = rows * feats;
+    for (int idx = tid; idx < total; idx += kTcThreads) staging[idx] = __ldg(src + idx);
+    __syncthreads();
+    // ---- thread <-> member row: convert to the operand format and write the canonical K-major layout
+    {
+      const float* row = staging + tid * feats;
+      const bool live = tid < rows;
+      for (int c = 0; c < chunks; ++c) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < kElemsPerChunk; ++e) {
+          const int k = c * kElemsPerChunk + e;
+          v[e] = (live && k < feats) ? row[k] : 0.f;
+        }
+        if (BF16) {
+          __nv_bfloat162 p[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          *reinterpret_cast<uint4*>(b_hi + c * kTcChunkBytes + tid * 16) = *reinterpret_cast<uint4*>(p);
+        } else {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(v[e]); lo[e] = v[e] - hi[e]; }
+          *reinterpret_cast<float4*>(b_hi + c * kTcChunkBytes + tid * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(b_lo + c * kTcChunkBytes + tid * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    // ---- one thread issues the MMAs; completion arrives on the mbarrier
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t off = ks * 2 * kTcChunkBytes;
+        if (BF16) {
+          umma_bf16(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
+        } else {
+          umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
+          umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bl + off), idesc, 1);
+          umma_tf32(tmem_base, umma_desc(al + off), umma_desc(bh + off), idesc, 1);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
+    }
+    mbar_wait(smem_u32(mbar), phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // ---- epilogue: lane = channel; walk the 128 columns (member rows) 32 at a time, pool per station
+    {
+      const int col = c0 + tid;
+      float sum = 0.f;
+      int cnt = 0, node = n0;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        if (q * 32 >= rows) break;
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (q * 32 + i < rows) {
+            sum += fmaxf(__uint_as_float(r[i]) + my_bias, 0.f);
+            if (++cnt == members) {                      // members are pooled in index order
+              if (col < hidden) pooled[(size_t)node * hidden + col] = sum;
+              sum = 0.f; cnt = 0; ++node;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();                                      // TMEM, staging and the B tile are free again
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128));
+}
+
+static size_t tc_smem_bytes(bool bf16, int feats, int chunks) {
+  const size_t op = (size_t)chunks * kTcChunkBytes;
+  return (bf16 ? 2 : 4) * op + (size_t)kTcRows * feats * sizeof(float) + 128 * sizeof(float) + 64;
+}
+
+// Is the tensor-core path applicable (and worth it) for this shape?
+bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("RC_DEEPSETS_TC");
+    forced = e ? (atoi(e) ? 1 : 2) : 0;                 // 1 = always when legal, 2 = never, 0 = by size
+  }
+  const bool legal = members >= 1 && members <= kTcRows && feats >= 1 && feats <= 64 && hidden >= 1;
+  if (!legal || forced == 2 || recording()) return false;
+  if (forced == 1) return true;
+  return (long long)num_nodes * members >= 65536 && hidden % 128 == 0;
+}
+
+int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
+                           int members, int feats, int hidden, cudaStream_t s) {
+  const int kp = bf16 ? ((feats + 15) / 16) * 16 : ((feats + 7) / 8) * 8;
+  const int chunks = bf16 ? kp / 8 : kp / 4;
+  const size_t smem = tc_smem_bytes(bf16, feats, chunks);
+  const int npt = kTcRows / members;
+  const int n_tiles = ceil_div(num_nodes, npt);
+  int gx = 2 * kNumSMs;
+  if (gx > n_tiles) gx = n_tiles;
+  dim3 grid(gx, ceil_div(hidden, 128));
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[bf16]) {
+    cudaError_t e = bf16 ? cudaFuncSetAttribute(deepsets_pool_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(deepsets_pool_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core path: %s", cudaGetErrorString(e));
+    attr[bf16] = smem;
+  }
+  if (bf16) deepsets_pool_fwd_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks);
+  else deepsets_pool_fwd_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks);
+  return check_launch("deepsets_pool_fwd_tc_kernel");
+}
+
+}  // namespace rc

@@ -380,3 +380,38 @@ def test_gine_aggregation_large_graph_path(dev, h):
     assert rel_err(_np(dx), x.grad.numpy()) < TOL
     assert rel_err(_np(dw), w.grad.numpy()) < TOL and rel_err(_np(db), b.grad.numpy()) < TOL
     assert rel_err(_np(de), eps.grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("m,em,f,h", [(2000, 51, 35, 128), (6500, 11, 35, 128), (1500, 51, 35, 256), (3000, 30, 20, 128)])
+def test_deepsets_tensor_core_path_fp32(dev, m, em, f, h):
+    """>= 65 536 member rows: rc_deepsets_pool_fwd runs on tcgen05 with the 3xTF32 split; still held to 1e-5."""
+    from raincast_gnn_b200 import _lib
+    g = torch.Generator().manual_seed(m + em)
+    ens = torch.randn(m, em, f, generator=g)
+    w1 = (torch.rand(h, f, generator=g) * 2 - 1) / f ** 0.5
+    b1 = torch.randn(h, generator=g) * 0.1
+    want = torch.relu(ens.double() @ w1.double().T + b1.double()).sum(1)
+    ed, wd, bd = ens.to(dev), w1.to(dev), b1.to(dev)
+    out = torch.empty(m, h, device=dev)
+    _lib.check(_lib.lib().rc_deepsets_pool_fwd(ed.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), m, em, f, h,
+                                               torch.cuda.current_stream().cuda_stream))
+    assert rel_err(_np(out), want.numpy()) < TOL
+
+
+@pytest.mark.parametrize("m,em,f,h", [(2000, 51, 35, 512), (977, 11, 35, 128), (64, 10, 35, 512), (300, 128, 64, 128)])
+def test_deepsets_tensor_core_path_bf16(dev, m, em, f, h):
+    """BASELINE.json config 5: bf16 operands, fp32 accumulate / pool / output; 1e-2 against the float64 oracle."""
+    from raincast_gnn_b200 import _lib
+    g = torch.Generator().manual_seed(m + em + h)
+    ens = torch.randn(m, em, f, generator=g)
+    w1 = (torch.rand(h, f, generator=g) * 2 - 1) / f ** 0.5
+    b1 = torch.randn(h, generator=g) * 0.1
+    want = torch.relu(ens.double() @ w1.double().T + b1.double()).sum(1)
+    ed, wd, bd = ens.to(dev), w1.to(dev), b1.to(dev)
+    out = torch.empty(m, h, device=dev)
+    _lib.check(_lib.lib().rc_deepsets_pool_fwd_bf16(ed.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), m, em, f, h,
+                                                    torch.cuda.current_stream().cuda_stream))
+    assert rel_err(_np(out), want.numpy()) < 1e-2
+    # and exactly what bf16 operands with fp32 accumulation should give (operands rounded, products exact)
+    ref = torch.relu(ens.bfloat16().double() @ w1.bfloat16().double().T + b1.double()).sum(1)
+    assert rel_err(_np(out), ref.numpy()) < 1e-5
