@@ -199,7 +199,9 @@ int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, const float* b1
  * partials[nblocks][H*F + H]. */
 int rc_deepsets_pool_bwd_nblocks(int num_nodes, int hidden);
 int rc_deepsets_pool_bwd(const float* ens, const float* w1, const float* b1, const float* d_pooled,
-                         float* partials, int num_nodes, int members, int feats, int hidden, void* stream);
+                         float* partials, int num_nodes, int members, int feats, int hidden,
+                         int bf16_operands /* 1 after rc_deepsets_pool_fwd_bf16: mask and inputs as the tensor cores saw them */,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Output links + closed-form CRPS (models/model_utils.py:70-113, models/loss.py:6-68,71-272,335-369)

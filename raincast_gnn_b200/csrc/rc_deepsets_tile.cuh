@@ -1,5 +1,7 @@
 // DeepSets pool tile functions shared by rc_deepsets.cu and the step program (rc_prog.cu).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "rc_common.cuh"
 
 namespace rc {
@@ -26,7 +28,12 @@ struct DsBwdP {
   int members;
   int feats;
   int hidden;
+  int bf16_operands;   // forward ran with bf16 operands: recompute the ReLU mask (and use the inputs) as the tensor cores saw them
 };
+
+__device__ __forceinline__ float round_operand(float v, int bf16) {
+  return bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : v;
+}
 
 
 
@@ -149,6 +156,7 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
   int members = p.members;
   int feats = p.feats;
   int hidden = p.hidden;
+  const int bf16_operands = p.bf16_operands;
   (void)bid; (void)gdim;
 
   constexpr int FP = 8 * KQ;
@@ -161,7 +169,8 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
   const int c0 = bid.y * kDsCols;
   for (int j = tid; j < kDsCols; j += kDsThreads) {
     const int col = c0 + j;
-    for (int k = 0; k < FP; ++k) Ws[k * kDsCols + j] = (col < hidden && k < feats) ? __ldg(w1 + (size_t)col * feats + k) : 0.f;
+    for (int k = 0; k < FP; ++k)
+      Ws[k * kDsCols + j] = (col < hidden && k < feats) ? round_operand(__ldg(w1 + (size_t)col * feats + k), bf16_operands) : 0.f;
     bias[j] = col < hidden ? __ldg(b1 + col) : 0.f;
   }
   const float4 bv_dummy = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -180,7 +189,7 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
     const float* src = ens + (size_t)row0 * feats;
     for (int idx = tid; idx < ROWS * FP; idx += kDsThreads) {
       const int r = idx / FP, k = idx - r * FP;
-      Es[idx] = (r < nrows && k < feats) ? __ldg(src + (size_t)r * feats + k) : 0.f;
+      Es[idx] = (r < nrows && k < feats) ? round_operand(__ldg(src + (size_t)r * feats + k), bf16_operands) : 0.f;
     }
     __syncthreads();
     // phase 1

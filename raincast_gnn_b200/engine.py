@@ -128,7 +128,7 @@ class TrainEngine:
     def _fwd_bwd_body(self):
         blk = self._blocks
         Pd, Gd = blk["ds"]
-        emb, s_ds = K.deepsets_fwd(Pd, self.ens)
+        emb, s_ds = K.deepsets_fwd(Pd, self.ens, bf16=(getattr(self.model.deepset, "compute_dtype", "fp32") == "bf16"))
         Pr, Gr = blk["dr"]
         node, s_dr = K.dimred_fwd(Pr, self.x, emb)
         saved = []

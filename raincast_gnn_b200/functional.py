@@ -23,9 +23,9 @@ class DeepSetsFn(Function):
     NAMES = ("phi0_w", "phi0_b", "phi2_w", "phi2_b", "rho0_w", "rho0_b", "rho2_w", "rho2_b")
 
     @staticmethod
-    def forward(ctx, ens, *params):
+    def forward(ctx, ens, bf16, *params):
         P = {n: _prep(p) for n, p in zip(DeepSetsFn.NAMES, params)}
-        emb, saved = K.deepsets_fwd(P, _prep(ens))
+        emb, saved = K.deepsets_fwd(P, _prep(ens), bf16=bf16)
         ctx.P, ctx.saved = P, saved
         return emb
 
@@ -34,7 +34,7 @@ class DeepSetsFn(Function):
         P = ctx.P
         G = {n: torch.empty_like(P[n]) for n in DeepSetsFn.NAMES}
         K.deepsets_bwd(P, ctx.saved, _lib.f32c(d_emb), G)
-        return (None,) + tuple(G[n] for n in DeepSetsFn.NAMES)
+        return (None, None) + tuple(G[n] for n in DeepSetsFn.NAMES)
 
 
 class DimRedFn(Function):

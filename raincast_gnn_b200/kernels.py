@@ -195,22 +195,24 @@ def linear_bwd_weight(dy_op: _lib.rc_operand, x_op: _lib.rc_operand, m, n, k, dw
 
 
 # --------------------------------------------------------------------------------------------- DeepSets
-def deepsets_fwd(P, ens):
-    """rho(sum_e phi(ens[:, e])) with the second phi Linear hoisted behind the sum (models/gnn.py:64-68)."""
+def deepsets_fwd(P, ens, bf16: bool = False):
+    """rho(sum_e phi(ens[:, e])) with the second phi Linear hoisted behind the sum (models/gnn.py:64-68).
+    bf16=True: the member contraction runs with bf16 operands / fp32 accumulation on the tensor cores (config 5)."""
     m, em, f = ens.shape
     h = P["phi0_w"].shape[0]
     L = _lib.lib()
     pooled = _new((m, h), torch.float32, ens.device)
-    _lib.check(L.rc_deepsets_pool_fwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), pooled.data_ptr(),
-                                      m, em, f, h, _stream(ens)), "rc_deepsets_pool_fwd")
+    fn = L.rc_deepsets_pool_fwd_bf16 if bf16 else L.rc_deepsets_pool_fwd
+    _lib.check(fn(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), pooled.data_ptr(),
+                  m, em, f, h, _stream(ens)), "rc_deepsets_pool_fwd")
     s2 = linear_fwd(pooled, P["phi2_w"], P["phi2_b"], bias_scale=float(em))       # sum_e (h_e W^T + b)
     r1 = linear_fwd(s2, P["rho0_w"], P["rho0_b"], relu=True)
     emb = linear_fwd(r1, P["rho2_w"], P["rho2_b"])
-    return emb, (ens, pooled, s2, r1)
+    return emb, (ens, pooled, s2, r1, bf16)
 
 
 def deepsets_bwd(P, saved, d_emb, G):
-    ens, pooled, s2, r1 = saved
+    ens, pooled, s2, r1, bf16 = saved
     m, em, f = ens.shape
     h = P["phi0_w"].shape[0]
     L = _lib.lib()
@@ -233,7 +235,7 @@ def deepsets_bwd(P, saved, d_emb, G):
     nb = int(L.rc_deepsets_pool_bwd_nblocks(m, h))
     part = _new((nb, h * f + h), torch.float32, dev)
     _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), d_pooled.data_ptr(),
-                                      part.data_ptr(), m, em, f, h, _stream(ens)), "rc_deepsets_pool_bwd")
+                                      part.data_ptr(), m, em, f, h, int(bf16), _stream(ens)), "rc_deepsets_pool_bwd")
     sink.add(part, G["phi0_w"], h * f + h, nb, h * f)
     sink.add(part.reshape(-1)[h * f:], G["phi0_b"], h * f + h, nb, h)
     with on_side(part):

@@ -70,11 +70,15 @@ class DeepSetEncoder(nn.Module):
                                  nn.Linear(hidden_channels, hidden_channels))
         self.rho = nn.Sequential(nn.Linear(hidden_channels, hidden_channels), nn.ReLU(),
                                  nn.Linear(hidden_channels, out_channels))
+        # "fp32" (reference numerics, 1e-5) or "bf16": member contraction with bf16 operands and fp32 accumulation
+        # on the tensor cores (BASELINE.json config 5, 1e-2); set as an attribute, the constructor keeps the
+        # reference signature
+        self.compute_dtype = "fp32"
 
     def forward(self, ensemble_feats):
         if ensemble_feats.dim() != 3:
             raise ValueError(f"ensemble must be [N, E, F], got {tuple(ensemble_feats.shape)}")
-        return F_rc.DeepSetsFn.apply(ensemble_feats, self.phi[0].weight, self.phi[0].bias, self.phi[2].weight,
+        return F_rc.DeepSetsFn.apply(ensemble_feats, self.compute_dtype == "bf16", self.phi[0].weight, self.phi[0].bias, self.phi[2].weight,
                                      self.phi[2].bias, self.rho[0].weight, self.rho[0].bias, self.rho[2].weight,
                                      self.rho[2].bias)
 
