@@ -82,7 +82,8 @@ RC_HD float crps_mixed_normal(const float* v, float y, float* g) {
 // against the hard switch (:268).  g[4] (d/du) is only meaningful when learn_u.
 RC_HD float crps_mixed(const float* v, float y, float xi, float t, bool learn_u, float* g) {
   const float mu = v[0], s = v[1], p = v[2], su = v[3], u = v[4], q = 1.0f - p;
-  const float zc = (kLogC - mu) / s, zu = (u - mu) / s, zy = (y - mu) / s;
+  const float inv_s = 1.0f / s, inv_su = 1.0f / su;     // one division per scale (the reference divides each time: <= 1 ulp apart)
+  const float zc = (kLogC - mu) * inv_s, zu = (u - mu) * inv_s, zy = (y - mu) * inv_s;
   const float Fc = norm_cdf(zc), Fu = norm_cdf(zu), Fy = norm_cdf(zy);
   const float fc = norm_pdf(zc), fu = norm_pdf(zu), fy = norm_pdf(zy);
   const float dF2 = norm_cdf(kSqrt2 * zu) - norm_cdf(kSqrt2 * zc);
@@ -96,12 +97,18 @@ RC_HD float crps_mixed(const float* v, float y, float xi, float t, bool learn_u,
   const float Uq = zu + 2.0f * q * fu - 2.0f * zu * Pu + A;          // upper / sigma
   const float inv2mx = 1.0f / (2.0f - xi), inv1mx = 1.0f / (1.0f - xi);
   const float tail_u_q = Pm * Pm * inv2mx;                           // tail(u) / sigma_u
-  const float x = (y - u) / su;
+  const float x = (y - u) * inv_su;
   float Tq, S = 0.0f, one_m_T = 0.0f;
   if (x > 0.0f) {
     const float base = 1.0f + xi * x;
-    S = powf(base, -1.0f / xi);                                      // GPD survival, models/loss.py:90
-    one_m_T = 1.0f - powf(base, -(1.0f - xi) / xi);                  // 1 - S^(1-xi)
+    if (xi == 0.5f) {                                                // every shipped params.json: S = base^-2, S^(1-xi) = base^-1
+      const float rb = 1.0f / base;
+      S = rb * rb;
+      one_m_T = 1.0f - rb;
+    } else {
+      S = powf(base, -1.0f / xi);                                    // GPD survival, models/loss.py:90
+      one_m_T = 1.0f - powf(base, -(1.0f - xi) / xi);                // 1 - S^(1-xi)
+    }
     Tq = x - 2.0f * Pm * inv1mx * one_m_T + tail_u_q;
   } else {
     Tq = fabsf(x) + tail_u_q;
@@ -126,8 +133,8 @@ RC_HD float crps_mixed(const float* v, float y, float xi, float t, bool learn_u,
   const float dTq = dL2 * su;
   // d tail(y) / d x:  1 - 2*Pm*S for x > 0 (T' = -(1-xi) S),  sign(x) otherwise (|x|' = 0 at 0)
   const float dx = dTq * (x > 0.0f ? 1.0f - 2.0f * Pm * S : (x < 0.0f ? -1.0f : 0.0f));
-  du += -dx / su;
-  dsu += -dx * x / su;
+  du += -dx * inv_su;
+  dsu += -dx * x * inv_su;
   const float dzy = dBq * cy;
   const float dzc = -dA * Pc * Pc;
   const float dzu = dA * Pu * Pu + dUq * (1.0f - 2.0f * Pu) - dPm * q * fu;
@@ -135,21 +142,39 @@ RC_HD float crps_mixed(const float* v, float y, float xi, float t, bool learn_u,
                      + 2.0f * fc * Pc + 2.0f * fu * Pu + 2.0f * q * kInvSqrtPi * dF2;
   g[2] = dBq * (2.0f * zy * (1.0f - Fy) - 2.0f * fy) + dA * dAdp
          + dUq * (-2.0f * fu + 2.0f * zu * (1.0f - Fu)) - dPm * (1.0f - Fu);
-  g[0] = -(dzy + dzc + dzu) / s;
-  g[1] = ds - (dzy * zy + dzc * zc + dzu * zu) / s;
+  g[0] = -(dzy + dzc + dzu) * inv_s;
+  g[1] = ds - (dzy * zy + dzc * zc + dzu * zu) * inv_s;
   g[3] = dsu;
-  g[4] = du + dzu / s;
+  g[4] = du + dzu * inv_s;
   return loss;
 }
 
 // One node: `row` holds post-processed (raw_input=0) or raw (raw_input=1) head outputs.
 // Writes the gradient w.r.t. `row` into g[0..width) (un-normalised) and returns the node loss.
-RC_HD float crps_node(const float* row, float y, int kind, int raw_input, float u_fixed, float xi, float t,
-                      float* g) {
+// In raw mode every link is evaluated once: value and derivative share the exponential.
+template <int kind>
+RC_HD float crps_node_k(const float* row, float y, int raw_input, float u_fixed, float xi, float t, float* g) {
   float v[5] = {0.f, 1.f, 0.f, 1.f, 0.f};
-  const int width = loss_width(kind);
+  float dlink[5] = {1.f, 1.f, 1.f, 1.f, 1.f};
+  constexpr int width = kind + 2;
+#ifdef __CUDACC__
+#pragma unroll
+#endif
   for (int i = 0; i < width; ++i) v[i] = row[i];
-  if (raw_input) apply_links(v, kind);
+  if (raw_input) {
+    {                                                     // sigma = softplus(r1) + 1e-6, d/dr = e/(1+e) (torch: threshold 20)
+      const float e = expf(v[1]);
+      dlink[1] = v[1] > 20.0f ? 1.0f : e / (1.0f + e);
+      v[1] = (v[1] > 20.0f ? v[1] : log1pf(e)) + kLinkEps;
+    }
+    if (kind >= 1) { const float sg = sigmoidf_(v[2]); v[2] = sg; dlink[2] = sg * (1.0f - sg); }
+    if (kind >= 2) {
+      const float e = expf(v[3]);
+      dlink[3] = v[3] > 20.0f ? 1.0f : e / (1.0f + e);
+      v[3] = (v[3] > 20.0f ? v[3] : log1pf(e)) + kLinkEps;
+    }
+    if (kind >= 3) { const float sg = sigmoidf_(v[4]); v[4] = sg * kUScale; dlink[4] = kUScale * sg * (1.0f - sg); }
+  }
   float loss;
   if (kind == RC_LOSS_NORMAL) {
     loss = crps_normal(v, y, g);
@@ -160,8 +185,22 @@ RC_HD float crps_node(const float* row, float y, int kind, int raw_input, float 
     if (!learn_u) v[4] = u_fixed;
     loss = crps_mixed(v, y, xi, t, learn_u, g);
   }
-  if (raw_input) links_backward(row, g, kind);
+  if (raw_input) {
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int i = 1; i < width; ++i) g[i] *= dlink[i];
+  }
   return loss;
+}
+
+RC_HD float crps_node(const float* row, float y, int kind, int raw_input, float u_fixed, float xi, float t, float* g) {
+  switch (kind) {
+    case RC_LOSS_NORMAL: return crps_node_k<RC_LOSS_NORMAL>(row, y, raw_input, u_fixed, xi, t, g);
+    case RC_LOSS_MIXED_NORMAL: return crps_node_k<RC_LOSS_MIXED_NORMAL>(row, y, raw_input, u_fixed, xi, t, g);
+    case RC_LOSS_MIXED: return crps_node_k<RC_LOSS_MIXED>(row, y, raw_input, u_fixed, xi, t, g);
+    default: return crps_node_k<RC_LOSS_MIXED_U>(row, y, raw_input, u_fixed, xi, t, g);
+  }
 }
 
 }  // namespace rc

@@ -124,7 +124,7 @@ __device__ __forceinline__ void crps_main_tile(const CrpsMainP& p, const uint3 b
     float row[WIDTH], g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < WIDTH; ++j) row[j] = pred[(size_t)i * WIDTH + j];
-    if (!isnan(yi)) loss = crps_node(row, yi, kind, raw_input, u_fixed, xi, t, g);
+    if (!isnan(yi)) loss = crps_node_k<WIDTH - 2>(row, yi, raw_input, u_fixed, xi, t, g);
     if (d_pred != nullptr) {
 #pragma unroll
       for (int j = 0; j < WIDTH; ++j) d_pred[(size_t)i * WIDTH + j] = g[j] * inv_n;

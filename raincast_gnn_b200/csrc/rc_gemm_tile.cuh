@@ -155,7 +155,9 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
     if (more) load_tile(t + 1);
     const float* as = As + cur * A_STAGE;
     const float* bs = Bs + cur * B_STAGE;
-#pragma unroll
+    // 8 reduction quads per unrolled body: the long-slice variant (32 quads) stays small enough for the instruction
+    // cache, which is cold at every launch of a step made of ~75 different small kernels
+#pragma unroll 8
     for (int r4 = 0; r4 < kRK / 4; ++r4) {
       float a[RM][4], b[4][4];   // a[i][rr], b[rr][j]
       if (AL == RC_A_ROW) {

@@ -11,23 +11,42 @@
 
 namespace rc {
 
-// one CTA per SM: 32 warps (64 registers each) for H = 128, 16 warps (128 registers) for wider rows
+// one CTA per SM: 32 warps (64 registers each) for H = 128, 16 warps (128 registers) for wider rows.
+// Measured alternatives at config 4 (forward): 24 warps with two batches of gathers in flight 143 us, 8 gathers per
+// warp with shuffle-broadcast indices 213 us, this version 109 us - resident warps beat per-warp pipelining here.
 __host__ __device__ constexpr int ranged_threads(int ch) { return ch == 1 ? 1024 : 512; }
+// compile-time knobs kept for experiments (measured on B200 at config 4, forward): unroll/threads/CTAs-per-SM
+//   4/1024/1: 109 us (default)   2/512/3: 134 us   3/512/3: 171 us   2/1024/2: 220 us   2/512/4: 225 us
+#ifndef RC_FWD_UNROLL
+#define RC_FWD_UNROLL 4
+#endif
+#ifndef RC_FWD_THREADS
+#define RC_FWD_THREADS 1024
+#endif
+#ifndef RC_FWD_MINB
+#define RC_FWD_MINB 1
+#endif
 constexpr int kRUnroll = 4;
 
+// Packed fp32x2 arithmetic (fma.rn.f32x2 / add.rn.f32x2, new on sm_100): one issue slot does two lanes of the
+// edge Linear, the message add and the accumulation; rounding is identical to the scalar sequence.
 __device__ __forceinline__ void relu_acc(float4& acc, float4 v, float a, float4 w, float4 b) {
-  acc.x += fmaxf(v.x + fmaf(a, w.x, b.x), 0.f);
-  acc.y += fmaxf(v.y + fmaf(a, w.y, b.y), 0.f);
-  acc.z += fmaxf(v.z + fmaf(a, w.z, b.z), 0.f);
-  acc.w += fmaxf(v.w + fmaf(a, w.w, b.w), 0.f);
+  const float2 a2 = make_float2(a, a);
+  float2 z0 = __fadd2_rn(make_float2(v.x, v.y), __ffma2_rn(a2, make_float2(w.x, w.y), make_float2(b.x, b.y)));
+  float2 z1 = __fadd2_rn(make_float2(v.z, v.w), __ffma2_rn(a2, make_float2(w.z, w.w), make_float2(b.z, b.w)));
+  z0.x = fmaxf(z0.x, 0.f); z0.y = fmaxf(z0.y, 0.f);
+  z1.x = fmaxf(z1.x, 0.f); z1.y = fmaxf(z1.y, 0.f);
+  const float2 s0 = __fadd2_rn(make_float2(acc.x, acc.y), z0), s1 = __fadd2_rn(make_float2(acc.z, acc.w), z1);
+  acc = make_float4(s0.x, s0.y, s1.x, s1.y);
 }
 
 template <int CH>
-__global__ void __launch_bounds__(ranged_threads(CH), 1)
+__global__ void __launch_bounds__(CH == 1 ? RC_FWD_THREADS : 512, CH == 1 ? RC_FWD_MINB : 1)
 gine_aggr_fwd_ranged_kernel(const float* __restrict__ x, const int* __restrict__ rowptr, const int* __restrict__ col,
                             const float* __restrict__ attr, const float* __restrict__ w_edge, const float* __restrict__ b_edge,
                             const float* __restrict__ eps_ptr, float* __restrict__ h, int m, int hidden, int rows_per_cta) {
-  constexpr int kRWarps = ranged_threads(CH) / 32;
+  constexpr int kRWarps = (CH == 1 ? RC_FWD_THREADS : 512) / 32;
+  constexpr int kRUnroll = CH == 1 ? RC_FWD_UNROLL : 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float self_scale = 1.0f + __ldg(eps_ptr);
   float4 w4[CH], b4[CH];
@@ -44,16 +63,26 @@ gine_aggr_fwd_ranged_kernel(const float* __restrict__ x, const int* __restrict__
     for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
     int s = beg;
+    int src_n[kRUnroll];
+    float a_n[kRUnroll];
+    if (s + kRUnroll <= end) {
+#pragma unroll
+      for (int k = 0; k < kRUnroll; ++k) { src_n[k] = __ldg(col + s + k); a_n[k] = __ldg(attr + s + k); }
+    }
     for (; s + kRUnroll <= end; s += kRUnroll) {
       int src[kRUnroll];
       float a[kRUnroll];
       float4 v[kRUnroll][CH];
 #pragma unroll
-      for (int k = 0; k < kRUnroll; ++k) { src[k] = __ldg(col + s + k); a[k] = __ldg(attr + s + k); }
+      for (int k = 0; k < kRUnroll; ++k) { src[k] = src_n[k]; a[k] = a_n[k]; }
 #pragma unroll
       for (int k = 0; k < kRUnroll; ++k)
 #pragma unroll
         for (int c = 0; c < CH; ++c) v[k][c] = ld4(xl + (size_t)src[k] * hidden + 128 * c);   // ld.global: allocate in L1
+      if (s + 2 * kRUnroll <= end) {                          // next batch's indices travel while this batch is summed
+#pragma unroll
+        for (int k = 0; k < kRUnroll; ++k) { src_n[k] = __ldg(col + s + kRUnroll + k); a_n[k] = __ldg(attr + s + kRUnroll + k); }
+      }
 #pragma unroll
       for (int k = 0; k < kRUnroll; ++k)                       // slot order = reference edge order
 #pragma unroll
@@ -79,13 +108,15 @@ gine_aggr_fwd_ranged_kernel(const float* __restrict__ x, const int* __restrict__
 }
 
 __device__ __forceinline__ void masked_acc(float4& acc, float4& acc_a, float4 g, float4 xj, float a, float4 w, float4 b) {
-  const float gx = (xj.x + fmaf(a, w.x, b.x) > 0.f) ? g.x : 0.f;
-  const float gy = (xj.y + fmaf(a, w.y, b.y) > 0.f) ? g.y : 0.f;
-  const float gz = (xj.z + fmaf(a, w.z, b.z) > 0.f) ? g.z : 0.f;
-  const float gw = (xj.w + fmaf(a, w.w, b.w) > 0.f) ? g.w : 0.f;
-  acc.x += gx; acc.y += gy; acc.z += gz; acc.w += gw;
-  acc_a.x = fmaf(gx, a, acc_a.x); acc_a.y = fmaf(gy, a, acc_a.y);
-  acc_a.z = fmaf(gz, a, acc_a.z); acc_a.w = fmaf(gw, a, acc_a.w);
+  const float2 a2 = make_float2(a, a);
+  const float2 z0 = __fadd2_rn(make_float2(xj.x, xj.y), __ffma2_rn(a2, make_float2(w.x, w.y), make_float2(b.x, b.y)));
+  const float2 z1 = __fadd2_rn(make_float2(xj.z, xj.w), __ffma2_rn(a2, make_float2(w.z, w.w), make_float2(b.z, b.w)));
+  const float2 g0 = make_float2(z0.x > 0.f ? g.x : 0.f, z0.y > 0.f ? g.y : 0.f);
+  const float2 g1 = make_float2(z1.x > 0.f ? g.z : 0.f, z1.y > 0.f ? g.w : 0.f);
+  const float2 s0 = __fadd2_rn(make_float2(acc.x, acc.y), g0), s1 = __fadd2_rn(make_float2(acc.z, acc.w), g1);
+  const float2 t0 = __ffma2_rn(g0, a2, make_float2(acc_a.x, acc_a.y)), t1 = __ffma2_rn(g1, a2, make_float2(acc_a.z, acc_a.w));
+  acc = make_float4(s0.x, s0.y, s1.x, s1.y);
+  acc_a = make_float4(t0.x, t0.y, t1.x, t1.y);
 }
 
 // dynamic shared memory: float red[kRWarps][2 * hidden] + float red_eps[kRWarps]
@@ -122,16 +153,26 @@ gine_aggr_bwd_ranged_kernel(const float* __restrict__ g, const float* __restrict
     }
     const int beg = __ldg(t_rowptr + row), end = __ldg(t_rowptr + row + 1);
     int q = beg;
+    int d_n[kRUnroll];
+    float a_n[kRUnroll];
+    if (q + kRUnroll <= end) {
+#pragma unroll
+      for (int k = 0; k < kRUnroll; ++k) { d_n[k] = __ldg(t_dst + q + k); a_n[k] = __ldg(t_attr + q + k); }
+    }
     for (; q + kRUnroll <= end; q += kRUnroll) {
       int d[kRUnroll];
       float a[kRUnroll];
       float4 v[kRUnroll][CH];
 #pragma unroll
-      for (int k = 0; k < kRUnroll; ++k) { d[k] = __ldg(t_dst + q + k); a[k] = __ldg(t_attr + q + k); }
+      for (int k = 0; k < kRUnroll; ++k) { d[k] = d_n[k]; a[k] = a_n[k]; }
 #pragma unroll
       for (int k = 0; k < kRUnroll; ++k)
 #pragma unroll
         for (int c = 0; c < CH; ++c) v[k][c] = ld4(gl + (size_t)d[k] * hidden + 128 * c);
+      if (q + 2 * kRUnroll <= end) {
+#pragma unroll
+        for (int k = 0; k < kRUnroll; ++k) { d_n[k] = __ldg(t_dst + q + kRUnroll + k); a_n[k] = __ldg(t_attr + q + kRUnroll + k); }
+      }
 #pragma unroll
       for (int k = 0; k < kRUnroll; ++k)
 #pragma unroll
@@ -185,13 +226,14 @@ gine_aggr_bwd_ranged_kernel(const float* __restrict__ g, const float* __restrict
 }
 
 int gine_ranged_grid(int m) { (void)m; return kNumSMs; }
+static int gine_fwd_grid() { return kNumSMs * RC_FWD_MINB; }
 
 int launch_gine_fwd_ranged(const float* x, const int* rowptr, const int* col, const float* attr, const float* w_edge,
                            const float* b_edge, const float* eps, float* h, int m, int hidden, cudaStream_t s) {
-  const int grid = gine_ranged_grid(m);
+  const int grid = hidden == 128 ? gine_fwd_grid() : gine_ranged_grid(m);
   const int rpc = ceil_div(m, grid);
   switch (hidden / 128) {
-    case 1: gine_aggr_fwd_ranged_kernel<1><<<grid, ranged_threads(1), 0, s>>>(x, rowptr, col, attr, w_edge, b_edge, eps, h, m, hidden, rpc); break;
+    case 1: gine_aggr_fwd_ranged_kernel<1><<<grid, RC_FWD_THREADS, 0, s>>>(x, rowptr, col, attr, w_edge, b_edge, eps, h, m, hidden, rpc); break;
     case 2: gine_aggr_fwd_ranged_kernel<2><<<grid, ranged_threads(2), 0, s>>>(x, rowptr, col, attr, w_edge, b_edge, eps, h, m, hidden, rpc); break;
     case 3: gine_aggr_fwd_ranged_kernel<3><<<grid, ranged_threads(3), 0, s>>>(x, rowptr, col, attr, w_edge, b_edge, eps, h, m, hidden, rpc); break;
     default: gine_aggr_fwd_ranged_kernel<4><<<grid, ranged_threads(4), 0, s>>>(x, rowptr, col, attr, w_edge, b_edge, eps, h, m, hidden, rpc); break;

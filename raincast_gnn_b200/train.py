@@ -1,12 +1,14 @@
 #!/usr/bin/env python3
-"""Caller of the hot path with train.py's command line, logging and checkpoint layout (train.py:30-38,97-216).
+"""Training entry point with the reference's command line (train.py:30-38), run-directory layout
+(<dir>/params.json, <dir>/logs/train_<run_id>.log, <dir>/models/run_<run_id>-best.ckpt) and epoch loop
+(train.py:55-91,198-208), driving the B200 kernels.
 
-    python -m raincast_gnn_b200.train --leadtime 24h --dir trained_models/24h_mixed_u --run_id 0 [--synthetic 64]
+    python -m raincast_gnn_b200.train --leadtime 24h --dir runs/24h_mixed_u --run_id 0 [--synthetic 64] [--engine]
 
-Identical flags to the reference; `--synthetic N` (new, optional) trains on N synthetic forecast dates of the
-reference shape instead of the EUPPBench files (which need network access to obtain).  `--engine` (new,
-optional) swaps the autograd loop for the CUDA-graph engine (same arithmetic, no per-step host sync); under
-torchrun it shards the dates over the ranks and all-reduces the gradients (DDP semantics).
+Additions (all optional): `--synthetic N` trains on N synthetic forecast dates of the reference shape (the
+EUPPBench files need network access), `--engine` replaces the autograd loop by the CUDA-graph engine (same
+arithmetic, no per-step host sync; under torchrun it shards the dates and all-reduces the gradients),
+`--max_epochs` overrides params.json.
 """
 from __future__ import annotations
 
@@ -19,8 +21,7 @@ import sys
 
 import numpy as np
 import torch
-from torch.optim import AdamW
-from torch.utils.data import random_split
+from torch.utils.data import Subset, random_split
 
 from . import dp
 from .engine import TrainEngine
@@ -28,151 +29,141 @@ from .models.gnn import GNN
 from .pyg_compat import DataLoader
 from .utils.dataset import EUPPBench, SyntheticEUPPBench
 
+LOG = logging.getLogger("raincast_gnn_b200.train")
+
 
 def parse_args(argv=None):
-    p = argparse.ArgumentParser(description="Train a graph-based model (B200 kernels behind the reference API).")
-    p.add_argument("--leadtime", type=str, default="24h")
-    p.add_argument("--dir", type=str, required=True, help="Directory containing params.json and for logs/checkpoints.")
-    p.add_argument("--run_id", type=str, required=True)
-    p.add_argument("--seed", type=int, default=42)
-    p.add_argument("--root_raw", type=str, default="data/EUPPBench/raw")
-    p.add_argument("--root_processed", type=str, default="data/EUPPBench/processed")
-    p.add_argument("--synthetic", type=int, default=0, help="train on this many synthetic dates (no dataset files needed)")
-    p.add_argument("--engine", action="store_true", help="use the CUDA-graph training engine")
-    p.add_argument("--max_epochs", type=int, default=None, help="override params.json max_epochs")
-    return p.parse_args(argv)
+    ap = argparse.ArgumentParser(description="Train the DeepSets + GINE post-processing model on B200 kernels.")
+    for flag, kw in (("--leadtime", dict(type=str, default="24h")),
+                     ("--dir", dict(type=str, required=True, help="run directory holding params.json")),
+                     ("--run_id", dict(type=str, required=True)),
+                     ("--seed", dict(type=int, default=42)),
+                     ("--root_raw", dict(type=str, default="data/EUPPBench/raw")),
+                     ("--root_processed", dict(type=str, default="data/EUPPBench/processed")),
+                     ("--synthetic", dict(type=int, default=0, help="number of synthetic dates (0: EUPPBench files)")),
+                     ("--max_epochs", dict(type=int, default=None))):
+        ap.add_argument(flag, **kw)
+    ap.add_argument("--engine", action="store_true", help="CUDA-graph training engine instead of autograd")
+    return ap.parse_args(argv)
 
 
-def set_seed(seed: int):
-    random.seed(seed)
-    np.random.seed(seed)
-    torch.manual_seed(seed)
+def seed_everything(seed: int):
+    """train.py:44-49."""
+    for fn in (random.seed, np.random.seed, torch.manual_seed):
+        fn(seed)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(seed)
 
 
-def train_one_epoch(model, loader, optimizer, device, logger):
-    """train.py:55-74, with the per-step `.item()` sync replaced by one device-side accumulator read per epoch."""
+def _open_log(run_dir: str, run_id: str, rank: int):
+    os.makedirs(os.path.join(run_dir, "logs"), exist_ok=True)
+    sinks = [logging.StreamHandler(sys.stdout)]
+    if rank == 0:
+        sinks.append(logging.FileHandler(os.path.join(run_dir, "logs", f"train_{run_id}.log"), mode="w"))
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s [%(levelname)s] %(message)s", handlers=sinks, force=True)
+
+
+def run_epoch_autograd(model, loader, optimizer, device) -> float:
+    """One pass of train.py:55-74; the loss is accumulated on the device and read once."""
     model.train()
-    total = torch.zeros((), dtype=torch.float64, device=device)
+    acc = torch.zeros((), dtype=torch.float64, device=device)
     for batch in loader:
         batch = batch.to(device)
-        preds = model(batch)
-        loss = model.loss_fn.crps(preds, batch.y)
+        loss = model.loss_fn.crps(model(batch), batch.y)
         optimizer.zero_grad()
         loss.backward()
         optimizer.step()
-        total += loss.detach()
-    avg = total.item() / max(len(loader), 1)
-    logger.info(f"  [Train] Loss: {avg:.6f}")
-    return avg
+        acc += loss.detach()
+    return acc.item() / max(len(loader), 1)
 
 
-def train_one_epoch_engine(engine, loader, logger):
-    """Same epoch through the graphed engine: H2D of x / ensemble / y, graph replay, all-reduce, fused AdamW."""
+def run_epoch_engine(engine: TrainEngine, loader) -> float:
+    """The same pass through the captured step: H2D of x / ensemble / y, replay, (all-reduce,) fused AdamW."""
     engine.loss_sum.zero_()
-    steps = 0
+    done = 0
     for batch in loader:
-        if batch.x.shape[0] != engine.m:          # ragged last batch: the captured graph has a fixed shape
-            continue
-        engine.load_batch(batch.x, batch.ensemble, batch.y)
-        engine.step()
-        steps += 1
-    avg = engine.loss_sum.item() / max(steps, 1)
-    logger.info(f"  [Train] Loss: {avg:.6f}")
-    return avg
+        if batch.x.shape[0] == engine.m:        # the captured step has a fixed shape: a ragged last batch is skipped
+            engine.load_batch(batch.x, batch.ensemble, batch.y)
+            engine.step()
+            done += 1
+    return engine.loss_sum.item() / max(done, 1)
 
 
-def evaluate(model, loader, device, logger):
-    """train.py:76-91."""
+@torch.no_grad()
+def validate(model, loader, device) -> float:
+    """train.py:76-91 (BatchNorm on running statistics)."""
     model.eval()
-    total = torch.zeros((), dtype=torch.float64, device=device)
-    with torch.no_grad():
-        for batch in loader:
-            batch = batch.to(device)
-            total += model.loss_fn.crps(model(batch), batch.y)
-    avg = total.item() / max(len(loader), 1)
-    logger.info(f"  [Val] Loss: {avg:.6f}")
-    return avg
+    acc = torch.zeros((), dtype=torch.float64, device=device)
+    for batch in loader:
+        batch = batch.to(device)
+        acc += model.loss_fn.crps(model(batch), batch.y)
+    return acc.item() / max(len(loader), 1)
 
 
 def main(argv=None):
     args = parse_args(argv)
     rank, local_rank, world = dp.env_world()
-    os.makedirs(os.path.join(args.dir, "logs"), exist_ok=True)
-    handlers = [logging.StreamHandler(sys.stdout)]
-    if rank == 0:
-        handlers.append(logging.FileHandler(os.path.join(args.dir, "logs", f"train_{args.run_id}.log"), mode="w"))
-    logging.basicConfig(level=logging.INFO, format="%(asctime)s [%(levelname)s] %(message)s", handlers=handlers, force=True)
-    logger = logging.getLogger(__name__)
-    logger.info("========== Training Script Started ==========")
-    logger.info(f"Arguments: {args}")
-    set_seed(args.seed)
-    config_path = os.path.join(args.dir, "params.json")
-    if not os.path.isfile(config_path):
-        logger.error(f"Could not find params.json at: {config_path}")
+    _open_log(args.dir, args.run_id, rank)
+    LOG.info("training run %s in %s: %s", args.run_id, args.dir, vars(args))
+    seed_everything(args.seed)
+    cfg_file = os.path.join(args.dir, "params.json")
+    if not os.path.isfile(cfg_file):
+        LOG.error("params.json is missing from %s", args.dir)
         sys.exit(1)
-    with open(config_path) as f:
-        config = json.load(f)
-    logger.info(f"Loaded config: {config}")
+    with open(cfg_file) as fh:
+        cfg = json.load(fh)
+    LOG.info("params.json: %s", cfg)
     if not torch.cuda.is_available():
-        logger.error("A CUDA device is required: this implementation has no CPU path.")
+        LOG.error("no CUDA device: this implementation has no CPU path")
         sys.exit(1)
     group = dp.init_from_env("nccl")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
 
+    max_dist = cfg.get("max_dist", 100.0)
     if args.synthetic > 0:
-        dataset = SyntheticEUPPBench(n_dates=args.synthetic, max_dist=config.get("max_dist", 100.0), seed=args.seed)
+        full = SyntheticEUPPBench(n_dates=args.synthetic, max_dist=max_dist, seed=args.seed)
     else:
-        dataset = EUPPBench(root_raw=args.root_raw, root_processed=args.root_processed, leadtime=args.leadtime,
-                            max_dist=config.get("max_dist", 100.0), split="train_rf")
-    n_total = len(dataset)
-    n_val = int(0.1 * n_total)
-    train_set, val_set = random_split(dataset, [n_total - n_val, n_val])
-    if world > 1:                                  # forecast dates sharded rank::world, same count on every rank
-        mine = dp.shard_dates(len(train_set), rank, world, seed=args.seed)
-        train_set = torch.utils.data.Subset(train_set, mine)
-    logger.info(f"Dataset sizes => Train: {len(train_set)}, Val: {len(val_set)}")
-    train_loader = DataLoader(train_set, batch_size=config["batch_size"], shuffle=True)
-    val_loader = DataLoader(val_set, batch_size=config["batch_size"], shuffle=False)
+        full = EUPPBench(root_raw=args.root_raw, root_processed=args.root_processed, leadtime=args.leadtime,
+                         max_dist=max_dist, split="train_rf")
+    held_out = int(0.1 * len(full))                                  # 90/10 split, train.py:149-153
+    fit_part, val_part = random_split(full, [len(full) - held_out, held_out])
+    if world > 1:                                                    # dates rank::world, equal counts per rank
+        fit_part = Subset(fit_part, dp.shard_dates(len(fit_part), rank, world, seed=args.seed))
+    LOG.info("dates: %d to fit, %d held out", len(fit_part), len(val_part))
+    bs = cfg["batch_size"]
+    fit_loader, val_loader = DataLoader(fit_part, batch_size=bs, shuffle=True), DataLoader(val_part, batch_size=bs)
 
-    example = train_set[0]
-    model = GNN(in_channels=example.x.shape[1], hidden_channels_gnn=config["gnn_hidden"], out_channels_gnn=config["gnn_hidden"],
-                num_layers_gnn=config["gnn_layers"], optimizer_class=AdamW, optimizer_params={"lr": config["lr"]},
-                loss=config["loss"], grad_u=config["grad_u"], u=config["u"], xi=config["xi"]).to(device)
-    with torch.no_grad():                          # train.py:182-183: one forward on a single un-batched graph
-        model(example.to(device))
-    max_epochs = args.max_epochs or config["max_epochs"]
+    probe = fit_part[0]
+    model = GNN(in_channels=probe.x.shape[1], hidden_channels_gnn=cfg["gnn_hidden"], out_channels_gnn=cfg["gnn_hidden"],
+                num_layers_gnn=cfg["gnn_layers"], optimizer_class=torch.optim.AdamW, optimizer_params={"lr": cfg["lr"]},
+                loss=cfg["loss"], grad_u=cfg["grad_u"], u=cfg["u"], xi=cfg["xi"]).to(device)
+    with torch.no_grad():
+        model(probe.to(device))          # the reference's pre-training forward on one un-batched graph (train.py:182-183)
     engine = optimizer = None
     if args.engine:
-        first = next(iter(train_loader))
+        first = next(iter(fit_loader))
         engine = TrainEngine(model, first.station_graph, first.x.shape[0], first.ensemble.shape[1], first.x.shape[1],
-                             lr=config["lr"], process_group=group).capture()
+                             lr=cfg["lr"], process_group=group).capture()
+    elif world > 1:
+        raise SystemExit("data-parallel training needs --engine (the gradient all-reduce lives in the engine)")
     else:
-        if world > 1:
-            raise SystemExit("data-parallel training needs --engine (the gradient all-reduce lives in the engine)")
         optimizer = model.optimizer_class(model.parameters(), **model.optimizer_params)
 
-    ckpt_dir = os.path.join(args.dir, "models")
-    os.makedirs(ckpt_dir, exist_ok=True)
-    best_val, best_path = float("inf"), None
-    logger.info(f"Starting training for {max_epochs} epochs...")
-    for epoch in range(1, max_epochs + 1):
-        logger.info(f"=== Epoch {epoch}/{max_epochs} ===")
-        if engine is not None:
-            train_one_epoch_engine(engine, train_loader, logger)
-        else:
-            train_one_epoch(model, train_loader, optimizer, device, logger)
-        val_loss = evaluate(model, val_loader, device, logger) if len(val_set) else float("nan")
-        if rank == 0 and (val_loss < best_val or best_path is None):
-            best_val = val_loss
-            best_path = os.path.join(ckpt_dir, f"run_{args.run_id}-best.ckpt")
-            torch.save(model.state_dict(), best_path)          # bare state_dict, train.py:207
-            logger.info(f"[Checkpoint] New best val_loss: {val_loss:.6f}. Saved to {best_path}")
-    logger.info("Training completed.")
-    logger.info("========== Training Script Finished ==========")
-    return best_path
+    os.makedirs(os.path.join(args.dir, "models"), exist_ok=True)
+    target = os.path.join(args.dir, "models", f"run_{args.run_id}-best.ckpt")
+    best, saved = float("inf"), None
+    n_epochs = args.max_epochs or cfg["max_epochs"]
+    for epoch in range(1, n_epochs + 1):
+        fit_loss = run_epoch_engine(engine, fit_loader) if engine is not None else run_epoch_autograd(model, fit_loader, optimizer, device)
+        val_loss = validate(model, val_loader, device) if len(val_part) else float("nan")
+        LOG.info("epoch %d/%d  [Train] Loss: %.6f  [Val] Loss: %.6f", epoch, n_epochs, fit_loss, val_loss)
+        if rank == 0 and (val_loss < best or saved is None):
+            best, saved = val_loss, target
+            torch.save(model.state_dict(), target)                   # bare state_dict, train.py:207
+            LOG.info("[Checkpoint] val %.6f -> %s", val_loss, target)
+    LOG.info("done; best checkpoint: %s", saved)
+    return saved
 
 
 if __name__ == "__main__":
