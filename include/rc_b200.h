@@ -94,6 +94,44 @@ int rc_gine_aggr_bwd(const float* g, const float* x, const int32_t* t_rowptr, co
 int rc_gine_aggr_bwd_finalize(const float* partials, int nblocks, int hidden, float* d_w, float* d_b,
                               float* d_eps, void* stream);
 
+/* Station tiles: the large-graph layout of the same aggregation (north_star item 1: the batching seam,
+ * utils/dataset.py / train.py:155-156, emits the graph layout the kernels want).  Rows of a gather matrix
+ * (rowptr/col/attr: the CSR above for forward, t_rowptr/t_dst/t_attr for backward) are clustered by a
+ * breadth-first search over the graph so that the distinct rows a cluster gathers (its own rows + a halo)
+ * number at most `max_src` and, with the cluster's row and edge records (at most `max_block_bytes`), fit in
+ * one CTA's shared memory; a batched reference graph becomes one tile per 122-station graph with no halo.
+ *   tile_stage_ptr[T+1] -> stage_id[]: the rows a tile stages, own rows first (tile order), halo after
+ *   tile_blk_ptr[T+1]   -> blocks[], in 16-byte units; per tile, 16-byte records:
+ *       {rows owned, rows staged, edges, 0}
+ *       per owned row {node id, byte offset of its first edge record inside the block, degree, 0}
+ *       edge records {staged-row index * row_bytes, float32 attr bits}, 8 bytes each, every row starting
+ *       on a 16-byte boundary; a row's edges keep CSR slot order.
+ * The builder takes worst-case output sizes (tile_*_ptr: M+1 ints, stage_id: M+E ints, blocks: 40*M + 8*E
+ * bytes) and reports the counts.  Fails with RC_ERR_ARG when a single row cannot fit a tile. */
+typedef struct rc_gine_tiles {
+  int32_t n_tiles; int32_t max_staged;       /* most rows any tile stages                      */
+  int32_t max_block_bytes; int32_t row_bytes; /* largest tile block; 4 * hidden                 */
+  const int32_t* tile_stage_ptr; const int32_t* tile_blk_ptr; const int32_t* stage_id; const int32_t* blocks;
+} rc_gine_tiles;
+/* max_src / max_block_bytes that fit one CTA at `hidden` columns (128 | hidden <= 512). */
+int rc_gine_tiles_limits(int hidden, int* max_src, int* max_block_bytes);
+int rc_gine_tiles_build_host(const int32_t* rowptr, const int32_t* col, const float* attr, int num_nodes,
+                             int64_t n_edges, int max_src, int max_block_bytes, int row_bytes,
+                             int32_t* tile_stage_ptr, int32_t* tile_blk_ptr, int32_t* stage_id, int32_t* blocks,
+                             int32_t* n_tiles, int64_t* n_staged, int64_t* n_block_units, int32_t* max_staged,
+                             int32_t* max_block_bytes_out);
+/* Same results as rc_gine_aggr_fwd / rc_gine_aggr_bwd, bit for bit in h and dx (same expressions, same
+ * summation order); every gathered row travels HBM/L2 -> shared memory once per tile (cp.async.bulk) and is
+ * read from shared memory by every edge that needs it.
+ * 128 | hidden <= 512.  partials: [rc_gine_aggr_bwd_tiled_nblocks][3][H], finalised by
+ * rc_gine_aggr_bwd_finalize. */
+int rc_gine_aggr_fwd_tiled(const float* x, const rc_gine_tiles* tiles, const float* w_edge, const float* b_edge,
+                           const float* eps, float* h, int num_nodes, int hidden, void* stream);
+int rc_gine_aggr_bwd_tiled_nblocks(const rc_gine_tiles* tiles, int hidden);
+int rc_gine_aggr_bwd_tiled(const float* g, const float* x, const rc_gine_tiles* t_tiles, const float* w_edge,
+                           const float* b_edge, const float* eps, const float* addend, float* dx, float* partials,
+                           int num_nodes, int hidden, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Dense layers: one fp32 SIMT GEMM family with fused prologues / epilogues (torch.nn.Linear,
  * BatchNorm1d and ReLU of models/gnn.py:21-26,51-62,113,123 and their backward)

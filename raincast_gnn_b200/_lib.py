@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librc_b200.so")
+LIB_PATH = os.environ.get("RC_B200_LIB") or os.path.join(_HERE, "csrc", "librc_b200.so")   # RC_B200_LIB: instrumented builds (tools/)
 
 RC_A_ROW, RC_A_RED = 0, 1
 RC_B_COL, RC_B_RED = 0, 1
@@ -27,6 +27,11 @@ class RcError(RuntimeError):
 
 class rc_csr(C.Structure):
     _fields_ = [(n, _fp) for n in ("rowptr", "col", "attr", "perm", "t_rowptr", "t_dst", "t_attr", "t_perm", "t_slot", "rev")]
+
+
+class rc_gine_tiles(C.Structure):
+    _fields_ = [("n_tiles", C.c_int32), ("max_staged", C.c_int32), ("max_block_bytes", C.c_int32), ("row_bytes", C.c_int32)] + [
+        (n, _fp) for n in ("tile_stage_ptr", "tile_blk_ptr", "stage_id", "blocks")]
 
 
 class rc_operand(C.Structure):
@@ -70,6 +75,11 @@ def _declare(lib):
         "rc_gine_aggr_bwd_nblocks": (i, [i, i]),
         "rc_gine_aggr_bwd": (i, [p, p, p, p, p, p, p, p, p, p, p, i, i, p]),
         "rc_gine_aggr_bwd_finalize": (i, [p, i, i, p, p, p, p]),
+        "rc_gine_tiles_limits": (i, [i, p, p]),
+        "rc_gine_tiles_build_host": (i, [p, p, p, i, ll, i, i, i, p, p, p, p, p, p, p, p, p]),
+        "rc_gine_aggr_fwd_tiled": (i, [p, C.POINTER(rc_gine_tiles), p, p, p, p, i, i, p]),
+        "rc_gine_aggr_bwd_tiled_nblocks": (i, [C.POINTER(rc_gine_tiles), i]),
+        "rc_gine_aggr_bwd_tiled": (i, [p, p, C.POINTER(rc_gine_tiles), p, p, p, p, p, p, i, i, p]),
         "rc_gemm_row_tile": (i, [C.POINTER(rc_gemm)]),
         "rc_gemm_run": (i, [C.POINTER(rc_gemm), p]),
         "rc_bn_stats_finalize": (i, [p, i, i, i, i, f, f, p, p, p, p, p, p]),

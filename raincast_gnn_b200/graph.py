@@ -40,6 +40,15 @@ class StationGraph:
     def device(self):
         return self.rowptr.device
 
+    def tiles(self, hidden: int):
+        """(forward, backward) StationTiles for rows of `hidden` floats, or None when the tiled kernels do not
+        apply (small graphs, unsupported width, a row gathering more rows than shared memory holds).  Built on
+        the host on first use and kept with the graph."""
+        cache = self.__dict__.setdefault("_tiles", {})
+        if hidden not in cache:
+            cache[hidden] = _build_tiles_pair(self, hidden)
+        return cache[hidden]
+
     def to(self, device, non_blocking: bool = False) -> "StationGraph":
         if torch.device(device) == self.device:
             return self
@@ -53,6 +62,78 @@ class StationGraph:
         inv = torch.empty(self.num_edges, dtype=torch.long, device=self.device)
         inv[self.perm.long()] = torch.arange(self.num_edges, device=self.device)
         return torch.stack([self.col.long(), rows])[:, inv]
+
+
+TILED_MIN_ROWS = 16384     # below this the warp-per-row kernels win (too few tiles to fill 148 SMs)
+
+
+class StationTiles:
+    """Tile-major layout of one gather matrix for rc_gine_aggr_{fwd,bwd}_tiled (include/rc_b200.h: rc_gine_tiles)."""
+    _ARRAYS = ("tile_stage_ptr", "tile_blk_ptr", "stage_id", "blocks")
+
+    def __init__(self, n_tiles: int, max_staged: int, max_block_bytes: int, row_bytes: int, num_rows: int, arrays: dict):
+        self.n_tiles, self.max_staged, self.max_block_bytes, self.row_bytes = n_tiles, max_staged, max_block_bytes, row_bytes
+        self.num_rows = num_rows
+        self.arrays = arrays
+        self.struct = _lib.rc_gine_tiles(n_tiles, max_staged, max_block_bytes, row_bytes,
+                                         *[arrays[a].data_ptr() for a in self._ARRAYS])
+
+    @property
+    def n_staged(self) -> int:
+        return int(self.arrays["stage_id"].numel())
+
+    @property
+    def n_halo(self) -> int:
+        """Staged rows that their tile does not own (0 for a batch of reference graphs)."""
+        return self.n_staged - self.num_rows
+
+    def to(self, device) -> "StationTiles":
+        return StationTiles(self.n_tiles, self.max_staged, self.max_block_bytes, self.row_bytes, self.num_rows,
+                            {k: v.to(device) for k, v in self.arrays.items()})
+
+
+def tile_limits(hidden: int):
+    """(max_src, max_block_bytes) one CTA can hold at `hidden` columns, or None when the width is unsupported."""
+    ms, mb = C.c_int(), C.c_int()
+    if _lib.lib().rc_gine_tiles_limits(int(hidden), C.addressof(ms), C.addressof(mb)) != 0:
+        return None
+    return ms.value, mb.value
+
+
+def build_tiles_host(rowptr: torch.Tensor, col: torch.Tensor, attr: torch.Tensor, max_src: int, max_block_bytes: int,
+                     row_bytes: int) -> StationTiles:
+    """rc_gine_tiles_build_host on host copies of a CSR (rowptr [M+1] int32, col [E] int32, attr [E] float32)."""
+    L = _lib.lib()
+    rowptr, col, attr = (t.detach().cpu().contiguous() for t in (rowptr, col, attr))
+    n, e = rowptr.numel() - 1, col.numel()
+    if e == 0:                                   # empty tensors have no storage address: give the C side one
+        col, attr = torch.zeros(1, dtype=torch.int32), torch.zeros(1)
+    tsp = torch.zeros(n + 1, dtype=torch.int32)
+    tbp = torch.zeros(n + 1, dtype=torch.int32)
+    stage = torch.empty(max(n + e, 1), dtype=torch.int32)
+    blocks = torch.empty(max(10 * n + 2 * e, 4), dtype=torch.int32)
+    nt, ms, mb = C.c_int32(), C.c_int32(), C.c_int32()
+    ns, nu = C.c_int64(), C.c_int64()
+    _lib.check(L.rc_gine_tiles_build_host(rowptr.data_ptr(), col.data_ptr(), attr.data_ptr(), n, e, int(max_src),
+                                          int(max_block_bytes), int(row_bytes), tsp.data_ptr(), tbp.data_ptr(),
+                                          stage.data_ptr(), blocks.data_ptr(), C.addressof(nt), C.addressof(ns),
+                                          C.addressof(nu), C.addressof(ms), C.addressof(mb)), "rc_gine_tiles_build_host")
+    arrays = {"tile_stage_ptr": tsp[:nt.value + 1].clone(), "tile_blk_ptr": tbp[:nt.value + 1].clone(),
+              "stage_id": stage[:ns.value].clone() if ns.value else torch.zeros(1, dtype=torch.int32)[:0],
+              "blocks": blocks[:max(4 * nu.value, 4)].clone()}
+    return StationTiles(nt.value, ms.value, mb.value, int(row_bytes), n, arrays)
+
+
+def _build_tiles_pair(g: "StationGraph", hidden: int):
+    lim = tile_limits(hidden)
+    if lim is None or g.num_nodes < TILED_MIN_ROWS:
+        return None
+    try:
+        fwd = build_tiles_host(g.rowptr, g.col, g.attr, lim[0], lim[1], 4 * hidden)
+        bwd = build_tiles_host(g.t_rowptr, g.t_dst, g.t_attr, lim[0], lim[1], 4 * hidden)
+    except _lib.RcError:
+        return None            # some row gathers more rows than one CTA can stage: the untiled kernels handle it
+    return fwd.to(g.device), bwd.to(g.device)
 
 
 def _alloc(num_nodes: int, num_edges: int, device) -> dict:

@@ -271,6 +271,47 @@ def dimred_bwd(P, saved, dy, G):
 
 
 # --------------------------------------------------------------------------------------------- GINE layer
+def gine_aggr_fwd(x, graph, lin_w, lin_b, eps, out, *, tiled=None):
+    """out = sum_{j -> i} relu(x_j + lin(e_ji)) + (1+eps) x_i  (PyG GINEConv message/aggregate, models/gnn.py:27-29).
+    Large graphs go through the station tiles (shared-memory staging), small ones through the warp-per-row kernel;
+    `tiled` forces the choice (tests)."""
+    L = _lib.lib()
+    m, h = x.shape
+    tiles = graph.tiles(h) if tiled is None or tiled else None
+    if tiled and tiles is None:
+        raise _lib.RcError("tiled GINE aggregation requested but no station tiles apply to this graph / width")
+    if tiles is not None:
+        _lib.check(L.rc_gine_aggr_fwd_tiled(x.data_ptr(), C.byref(tiles[0].struct), lin_w.data_ptr(), lin_b.data_ptr(),
+                                            eps.data_ptr(), out.data_ptr(), m, h, _stream(x)), "rc_gine_aggr_fwd_tiled")
+    else:
+        _lib.check(L.rc_gine_aggr_fwd(x.data_ptr(), graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.attr.data_ptr(),
+                                      lin_w.data_ptr(), lin_b.data_ptr(), eps.data_ptr(), out.data_ptr(), m, h, _stream(x)),
+                   "rc_gine_aggr_fwd")
+    return out
+
+
+def gine_aggr_bwd(g, x, graph, lin_w, lin_b, eps, addend, dx, *, tiled=None):
+    """dx and the per-block partials of d lin_w, d lin_b, d eps; returns (partials, nblocks)."""
+    L = _lib.lib()
+    m, h = x.shape
+    tiles = graph.tiles(h) if tiled is None or tiled else None
+    if tiled and tiles is None:
+        raise _lib.RcError("tiled GINE aggregation requested but no station tiles apply to this graph / width")
+    if tiles is not None:
+        nb = int(L.rc_gine_aggr_bwd_tiled_nblocks(C.byref(tiles[1].struct), h))
+        part = _new((nb, 3, h), torch.float32, x.device)
+        _lib.check(L.rc_gine_aggr_bwd_tiled(g.data_ptr(), x.data_ptr(), C.byref(tiles[1].struct), lin_w.data_ptr(),
+                                            lin_b.data_ptr(), eps.data_ptr(), _lib.ptr(addend), dx.data_ptr(), part.data_ptr(),
+                                            m, h, _stream(x)), "rc_gine_aggr_bwd_tiled")
+    else:
+        nb = int(L.rc_gine_aggr_bwd_nblocks(m, h))
+        part = _new((nb, 3, h), torch.float32, x.device)
+        _lib.check(L.rc_gine_aggr_bwd(g.data_ptr(), x.data_ptr(), graph.t_rowptr.data_ptr(), graph.t_dst.data_ptr(),
+                                      graph.t_attr.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr(), eps.data_ptr(),
+                                      _lib.ptr(addend), dx.data_ptr(), part.data_ptr(), m, h, _stream(x)), "rc_gine_aggr_bwd")
+    return part, nb
+
+
 def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     """One ResGnn layer (models/gnn.py:39-44): y = relu(conv(x)) for the first layer, x + relu(conv(x)) after;
     conv = GINEConv(nn = Linear - BatchNorm1d - ReLU - Linear)."""
@@ -279,9 +320,7 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     dev = x.device
     st = _stream(x)
     agg = _new_like(x)
-    _lib.check(L.rc_gine_aggr_fwd(x.data_ptr(), graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.attr.data_ptr(),
-                                  P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(), agg.data_ptr(),
-                                  m, h, st), "rc_gine_aggr_fwd")
+    gine_aggr_fwd(x, graph, P["lin_w"], P["lin_b"], P["eps"], agg)
     hid = P["nn0_w"].shape[0]
     t = _new((m, hid), torch.float32, dev)
     mean = _new(hid, torch.float32, dev)
@@ -345,12 +384,8 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     d_agg = _new((m, h), torch.float32, dev)
     gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
     # aggregation backward (+ residual branch of layers > 0)
-    nb = int(L.rc_gine_aggr_bwd_nblocks(m, h))
-    part = _new((nb, 3, h), torch.float32, dev)
     dx = _new((m, h), torch.float32, dev)
-    _lib.check(L.rc_gine_aggr_bwd(d_agg.data_ptr(), x.data_ptr(), graph.t_rowptr.data_ptr(), graph.t_dst.data_ptr(),
-                                  graph.t_attr.data_ptr(), P["lin_w"].data_ptr(), P["lin_b"].data_ptr(), P["eps"].data_ptr(),
-                                  None if first else dy.data_ptr(), dx.data_ptr(), part.data_ptr(), m, h, st), "rc_gine_aggr_bwd")
+    part, nb = gine_aggr_bwd(d_agg, x, graph, P["lin_w"], P["lin_b"], P["eps"], None if first else dy, dx)
     with on_side(part, d_agg):
         _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, G["lin_w"].data_ptr(), G["lin_b"].data_ptr(),
                                                G["eps"].data_ptr(), _stream(x)), "rc_gine_aggr_bwd_finalize")

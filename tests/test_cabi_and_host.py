@@ -145,3 +145,83 @@ def test_model_state_dict_layout_and_ctor_errors(golden_model):
         ResGnn(8, 8, 0, 8)                                            # models/gnn.py:13
     with pytest.raises(ValueError):
         MixedLoss(grad_u=False, xi=1.0, u=1.0)
+
+
+# ------------------------------------------------------------------------------------------------ station tiles
+def _check_tiles(sg_rowptr, sg_col, sg_attr, tiles, max_src, max_block, row_bytes=512):
+    """Invariants of rc_gine_tiles_build_host: a partition of the rows, at most max_src staged rows and max_block
+    record bytes per tile, and every row's edges recoverable in CSR slot order with bit-identical attributes."""
+    a = {k: v.numpy() for k, v in tiles.arrays.items()}
+    n = len(sg_rowptr) - 1
+    tsp, tbp, stage = a["tile_stage_ptr"], a["tile_blk_ptr"], a["stage_id"]
+    blocks = a["blocks"].reshape(-1, 4)
+    assert len(tsp) == tiles.n_tiles + 1 and tsp[0] == 0 and tsp[-1] == len(stage) and tbp[0] == 0
+    owned, staged_max, blk_max, edges = [], 0, 0, 0
+    for t in range(tiles.n_tiles):
+        blk = blocks[tbp[t]:tbp[t + 1]]
+        nrows, nst, ne, _ = blk[0]
+        staged = stage[tsp[t]:tsp[t + 1]]
+        assert nst == len(staged) <= max_src and len(np.unique(staged)) == nst and 16 * len(blk) <= max_block
+        staged_max, blk_max, edges = max(staged_max, nst), max(blk_max, 16 * len(blk)), edges + ne
+        words = blk.reshape(-1)
+        for r in range(nrows):
+            v, eoff, deg, _ = blk[1 + r]
+            assert v == staged[r] and eoff % 16 == 0          # own rows lead the stage list, in tile order
+            owned.append(v)
+            meta = words[eoff // 4: eoff // 4 + 2 * deg].reshape(-1, 2)
+            assert (meta[:, 0] % row_bytes == 0).all()
+            assert np.array_equal(staged[meta[:, 0] // row_bytes], sg_col[sg_rowptr[v]:sg_rowptr[v + 1]])
+            assert np.array_equal(meta[:, 1].view(np.uint32), sg_attr[sg_rowptr[v]:sg_rowptr[v + 1]].view(np.uint32))
+    assert np.array_equal(np.sort(np.array(owned, dtype=np.int64)), np.arange(n))
+    assert edges == len(sg_col)
+    assert staged_max == tiles.max_staged and blk_max == tiles.max_block_bytes
+
+
+def test_station_tiles_batched_reference_graph(golden_graph):
+    """A batch of reference graphs is block-diagonal: one tile per 122-station graph, no halo."""
+    ei, ea = golden_graph["ref122_d100.edge_index"], golden_graph["ref122_d100.edge_attr"]
+    batch = 12
+    ei_b, ea_b = og.collate_edges(ei, ea, 122, batch)
+    sg = G.build_station_graph(torch.from_numpy(ei_b), torch.from_numpy(ea_b), 122 * batch)
+    max_src, max_block = G.tile_limits(128)
+    assert max_src * 512 + max_block + 16 <= 227 * 512 - 1024 and max_src >= 160
+    for rp, col, attr in ((sg.rowptr, sg.col, sg.attr), (sg.t_rowptr, sg.t_dst, sg.t_attr)):
+        tiles = G.build_tiles_host(rp, col, attr, max_src, max_block, 512)
+        _check_tiles(rp.numpy(), col.numpy(), attr.numpy(), tiles, max_src, max_block)
+        assert tiles.n_tiles == batch and tiles.n_halo == 0 and tiles.max_staged == 122
+
+
+@pytest.mark.parametrize("n,deg,max_src,max_block", [(3000, 12.0, 64, 1 << 20), (5000, 29.0, 175, 25584), (400, 6.0, 40, 1024),
+                                                     (2000, 20.0, 200, 2048)])
+def test_station_tiles_radius_graph(n, deg, max_src, max_block):
+    coords = syn.station_coords(n, 300.0, seed=3)
+    ei, ea = G.radius_graph_from_coords(coords, syn.scaled_graph_radius(n, 300.0, deg))
+    sg = G.build_station_graph(ei, ea, n)
+    tiles = G.build_tiles_host(sg.rowptr, sg.col, sg.attr, max_src, max_block, 512)
+    _check_tiles(sg.rowptr.numpy(), sg.col.numpy(), sg.attr.numpy(), tiles, max_src, max_block)
+    # clusters are compact: each owned row brings well under its full neighbourhood in halo rows
+    assert tiles.n_halo < 0.5 * sg.num_edges
+
+
+def test_station_tiles_edge_cases():
+    # asymmetric graph with an isolated node, a multi-edge and no self loops
+    ei = torch.tensor([[0, 0, 1, 3, 3, 4], [1, 1, 2, 0, 2, 0]])
+    ea = torch.arange(6, dtype=torch.float32) + 1.0
+    sg = G.build_station_graph(ei, ea, 6)
+    for rp, col, attr in ((sg.rowptr, sg.col, sg.attr), (sg.t_rowptr, sg.t_dst, sg.t_attr)):
+        for max_src in (3, 4, 100):
+            tiles = G.build_tiles_host(rp, col, attr, max_src, 4096, 1024)
+            _check_tiles(rp.numpy(), col.numpy(), attr.numpy(), tiles, max_src, 4096, row_bytes=1024)
+    # a row that cannot fit: node 0 gathers {3, 4} plus itself = 3 staged rows > 2; or its records exceed the block
+    with pytest.raises(_lib.RcError):
+        G.build_tiles_host(sg.rowptr, sg.col, sg.attr, 2, 4096, 512)
+    star = G.build_station_graph(torch.tensor([[1, 2, 3, 4, 5], [0, 0, 0, 0, 0]]), torch.ones(5), 6)
+    with pytest.raises(_lib.RcError):          # header 16 + row record 16 + 3 edge records 48 = 80 bytes > 64
+        G.build_tiles_host(star.rowptr, star.col, star.attr, 100, 64, 512)
+    _check_tiles(star.rowptr.numpy(), star.col.numpy(), star.attr.numpy(),
+                 G.build_tiles_host(star.rowptr, star.col, star.attr, 100, 80, 512), 100, 80)
+    # empty graph
+    empty = G.build_station_graph(torch.zeros((2, 0), dtype=torch.int64), torch.zeros(0), 0)
+    tiles = G.build_tiles_host(empty.rowptr, empty.col, empty.attr, 8, 4096, 512)
+    assert tiles.n_tiles == 0 and tiles.n_staged == 0
+    assert G.tile_limits(100) is None and G.tile_limits(512)[0] >= 80

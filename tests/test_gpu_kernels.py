@@ -415,3 +415,87 @@ def test_deepsets_tensor_core_path_bf16(dev, m, em, f, h):
     # and exactly what bf16 operands with fp32 accumulation should give (operands rounded, products exact)
     ref = torch.relu(ens.bfloat16().double() @ w1.bfloat16().double().T + b1.double()).sum(1)
     assert rel_err(_np(out), ref.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ station tiles
+def _tiled_vs_untiled(dev, sg, m, h, seed, want=None):
+    """Runs both aggregation paths on the same inputs; h and dx must agree bit for bit (same expressions, same
+    summation order), the parameter gradients to rounding (different partial-sum grouping)."""
+    from raincast_gnn_b200 import kernels as K
+    g = torch.Generator().manual_seed(seed)
+    x, gout, add = (torch.randn(m, h, generator=g).to(dev) for _ in range(3))
+    w, b = torch.randn(h, generator=g).to(dev), torch.randn(h, generator=g).to(dev)
+    eps = torch.tensor([0.2], device=dev)
+    L = _lib_mod().lib()
+    outs = {}
+    for tiled in (False, True):
+        hh, dx = torch.empty(m, h, device=dev), torch.empty(m, h, device=dev)
+        K.gine_aggr_fwd(x, sg, w, b, eps, hh, tiled=tiled)
+        part, nb = K.gine_aggr_bwd(gout, x, sg, w, b, eps, add, dx, tiled=tiled)
+        dw, db, de = torch.empty(h, device=dev), torch.empty(h, device=dev), torch.empty(1, device=dev)
+        _lib_mod().check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, dw.data_ptr(), db.data_ptr(), de.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream))
+        outs[tiled] = (hh, dx, dw, db, de)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[True][0], outs[False][0]), "tiled forward differs from the warp-per-row kernel"
+    assert torch.equal(outs[True][1], outs[False][1]), "tiled backward dx differs from the warp-per-row kernel"
+    for i in (2, 3, 4):
+        assert rel_err(_np(outs[True][i]), _np(outs[False][i])) < TOL
+    return outs[True]
+
+
+def _lib_mod():
+    from raincast_gnn_b200 import _lib
+    return _lib
+
+
+@pytest.mark.parametrize("h", [128, 256, 512])
+def test_gine_tiled_radius_graph(dev, h):
+    """Station tiles on a 20k-node radius graph (mean degree 20): bitwise equal to the untiled kernels, and within
+    1e-5 of the float64 restatement of PyG's GINEConv on dyadic inputs (no unit near its ReLU threshold)."""
+    from raincast_gnn_b200 import graph as G, kernels as K
+    from raincast_gnn_b200.utils import synthetic as syn
+    m = 20_000
+    coords = syn.station_coords(m, 450.0, seed=2)
+    ei, ea = G.radius_graph_from_coords(coords, syn.scaled_graph_radius(m, 450.0, 20.0))
+    sg = G.build_station_graph(ei, ea, m).to(dev)
+    tiles = sg.tiles(h)
+    assert tiles is not None and tiles[0].n_tiles > 50 and tiles[0].max_staged <= G.tile_limits(h)[0]
+    _tiled_vs_untiled(dev, sg, m, h, seed=h)
+    # oracle comparison on dyadic data
+    g = torch.Generator().manual_seed(h + 1)
+
+    def dyadic(*shape, scale=8.0):
+        return torch.round(torch.randn(*shape, generator=g, dtype=torch.float64) * scale) / scale
+    ea2 = (torch.randint(1, 64, (ei.shape[1], 1), generator=g).double() / 4.0)
+    sg2 = G.build_station_graph(ei, ea2.float(), m).to(dev)
+    x, w, b = dyadic(m, h).requires_grad_(True), dyadic(h).requires_grad_(True), dyadic(h).requires_grad_(True)
+    eps = torch.tensor([-0.25], dtype=torch.float64, requires_grad=True)
+    gout = torch.randn(m, h, generator=g, dtype=torch.float64)
+    want = _gine_ref(x, ei, ea2, w, b, eps)
+    want.backward(gout)
+    xd, wd, bd, ed, gd = (t.detach().float().to(dev) for t in (x, w, b, eps, gout))
+    hh, dx = torch.empty(m, h, device=dev), torch.empty(m, h, device=dev)
+    K.gine_aggr_fwd(xd, sg2, wd, bd, ed, hh, tiled=True)
+    part, nb = K.gine_aggr_bwd(gd, xd, sg2, wd, bd, ed, None, dx, tiled=True)
+    dw, db, de = torch.empty(h, device=dev), torch.empty(h, device=dev), torch.empty(1, device=dev)
+    _lib_mod().check(_lib_mod().lib().rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, dw.data_ptr(), db.data_ptr(), de.data_ptr(),
+                                                               torch.cuda.current_stream().cuda_stream))
+    assert rel_err(_np(hh), want.detach().numpy()) < TOL
+    assert rel_err(_np(dx), x.grad.numpy()) < TOL
+    assert rel_err(_np(dw), w.grad.numpy()) < TOL and rel_err(_np(db), b.grad.numpy()) < TOL
+    assert rel_err(_np(de), eps.grad.numpy()) < TOL
+
+
+def test_gine_tiled_batched_reference_graphs(dev, golden_graph):
+    """160 reference graphs in one batch (19 520 stations): one tile per graph, no halo, bitwise equal results."""
+    from oracle import graph as og
+    from raincast_gnn_b200 import graph as G
+    ei, ea = golden_graph["ref122_d100.edge_index"], golden_graph["ref122_d100.edge_attr"]
+    batch = 160
+    ei_b, ea_b = og.collate_edges(ei, ea, 122, batch)
+    m = 122 * batch
+    sg = G.build_station_graph(torch.from_numpy(ei_b), torch.from_numpy(ea_b), m).to(dev)
+    tiles = sg.tiles(128)
+    assert tiles is not None and tiles[0].n_tiles == batch and tiles[0].n_halo == 0 and tiles[1].n_halo == 0
+    _tiled_vs_untiled(dev, sg, m, 128, seed=7)
