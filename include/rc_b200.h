@@ -98,16 +98,24 @@ int rc_gine_aggr_bwd_finalize(const float* partials, int nblocks, int hidden, fl
  * utils/dataset.py / train.py:155-156, emits the graph layout the kernels want).  Rows of a gather matrix
  * (rowptr/col/attr: the CSR above for forward, t_rowptr/t_dst/t_attr for backward) are clustered by a
  * breadth-first search over the graph so that the distinct rows a cluster gathers (its own rows + a halo)
- * number at most `max_src` and, with the cluster's row and edge records (at most `max_block_bytes`), fit in
- * one CTA's shared memory; a batched reference graph becomes one tile per 122-station graph with no halo.
- *   tile_stage_ptr[T+1] -> stage_id[]: the rows a tile stages, own rows first (tile order), halo after
+ * number at most `max_src` and, with the cluster's records (at most `max_block_bytes`), fit in one CTA's
+ * shared memory; a batched reference graph becomes one tile per 122-station graph with no halo.  Inside a
+ * tile, rows are grouped three by three (a row with the two neighbours sharing most sources with it) and a
+ * group's edges are stored per distinct source, so that a warp reads a gathered row from shared memory once
+ * for all rows of the group that use it.
+ *   tile_stage_ptr[T+1] -> stage_id[]: the rows a tile stages, own rows first (group by group), halo after
  *   tile_blk_ptr[T+1]   -> blocks[], in 16-byte units; per tile, 16-byte records:
- *       {rows owned, rows staged, edges, 0}
- *       per owned row {node id, byte offset of its first edge record inside the block, degree, 0}
- *       edge records {staged-row index * row_bytes, float32 attr bits}, 8 bytes each, every row starting
- *       on a 16-byte boundary; a row's edges keep CSR slot order.
- * The builder takes worst-case output sizes (tile_*_ptr: M+1 ints, stage_id: M+E ints, blocks: 40*M + 8*E
- * bytes) and reports the counts.  Fails with RC_ERR_ARG when a single row cannot fit a tile. */
+ *       {rows owned, rows staged, groups, edges}
+ *       per group {node id of row 0, 1, 2 (-1: none), byte offset of the group's first entry in the block}
+ *                 {n1 | n2 << 16, n3 | n4 << 16, n5 | n6 << 16, n7}  entries per class (class = bit mask of
+ *                                                                    the group's rows that use the source)
+ *                 {degree of row 0, 1, 2 (float32), byte offset of row 0 among the staged rows}
+ *       entries {staged-row index * row_bytes, attr for row 0, 1, 2 (float32 bits)}, class 1 first, 7 last;
+ *       groups with most edges first.  A repeated (source, row) pair gets one entry per occurrence.
+ * The builder takes worst-case output sizes (tile_*_ptr: M+1 ints, stage_id: M+E ints, blocks: 64*M + 16*E
+ * bytes) and reports the counts (n_entries: row reads from shared memory; E / n_entries = reuse factor).
+ * Fails with RC_ERR_ARG when a single row cannot fit a tile.  rc_gine_tiles_verify_host walks the tiles
+ * the way the kernels do and compares them with the CSR (RC_ERR_GRAPH + message on any difference). */
 typedef struct rc_gine_tiles {
   int32_t n_tiles; int32_t max_staged;       /* most rows any tile stages                      */
   int32_t max_block_bytes; int32_t row_bytes; /* largest tile block; 4 * hidden                 */
@@ -119,10 +127,15 @@ int rc_gine_tiles_build_host(const int32_t* rowptr, const int32_t* col, const fl
                              int64_t n_edges, int max_src, int max_block_bytes, int row_bytes,
                              int32_t* tile_stage_ptr, int32_t* tile_blk_ptr, int32_t* stage_id, int32_t* blocks,
                              int32_t* n_tiles, int64_t* n_staged, int64_t* n_block_units, int32_t* max_staged,
-                             int32_t* max_block_bytes_out);
-/* Same results as rc_gine_aggr_fwd / rc_gine_aggr_bwd, bit for bit in h and dx (same expressions, same
- * summation order); every gathered row travels HBM/L2 -> shared memory once per tile (cp.async.bulk) and is
- * read from shared memory by every edge that needs it.
+                             int32_t* max_block_bytes_out, int64_t* n_entries);
+int rc_gine_tiles_verify_host(const int32_t* rowptr, const int32_t* col, const float* attr, int num_nodes,
+                              int64_t n_edges, int n_tiles, int max_staged, int max_block_bytes, int row_bytes,
+                              const int32_t* tile_stage_ptr, const int32_t* tile_blk_ptr, const int32_t* stage_id,
+                              const int32_t* blocks);
+/* Same results as rc_gine_aggr_fwd / rc_gine_aggr_bwd to rounding (the sums run class by class instead of in
+ * CSR slot order, and relu(x_j + a w + b) is evaluated as max(x_j + a w, -b) + b with the bias added once per
+ * row); deterministic for given tiles.  Every gathered row travels HBM/L2 -> shared memory once per tile
+ * (cp.async) and is read from shared memory once per group of rows that needs it.
  * 128 | hidden <= 512.  partials: [rc_gine_aggr_bwd_tiled_nblocks][3][H], finalised by
  * rc_gine_aggr_bwd_finalize. */
 int rc_gine_aggr_fwd_tiled(const float* x, const rc_gine_tiles* tiles, const float* w_edge, const float* b_edge,

@@ -76,7 +76,8 @@ def _declare(lib):
         "rc_gine_aggr_bwd": (i, [p, p, p, p, p, p, p, p, p, p, p, i, i, p]),
         "rc_gine_aggr_bwd_finalize": (i, [p, i, i, p, p, p, p]),
         "rc_gine_tiles_limits": (i, [i, p, p]),
-        "rc_gine_tiles_build_host": (i, [p, p, p, i, ll, i, i, i, p, p, p, p, p, p, p, p, p]),
+        "rc_gine_tiles_build_host": (i, [p, p, p, i, ll, i, i, i, p, p, p, p, p, p, p, p, p, p]),
+        "rc_gine_tiles_verify_host": (i, [p, p, p, i, ll, i, i, i, i, p, p, p, p]),
         "rc_gine_aggr_fwd_tiled": (i, [p, C.POINTER(rc_gine_tiles), p, p, p, p, i, i, p]),
         "rc_gine_aggr_bwd_tiled_nblocks": (i, [C.POINTER(rc_gine_tiles), i]),
         "rc_gine_aggr_bwd_tiled": (i, [p, p, C.POINTER(rc_gine_tiles), p, p, p, p, p, p, i, i, p]),

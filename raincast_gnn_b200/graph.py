@@ -44,10 +44,12 @@ class StationGraph:
         """(forward, backward) StationTiles for rows of `hidden` floats, or None when the tiled kernels do not
         apply (small graphs, unsupported width, a row gathering more rows than shared memory holds).  Built on
         the host on first use and kept with the graph."""
+        if hidden < 128 or hidden % 128 or hidden > 512:
+            return None
         cache = self.__dict__.setdefault("_tiles", {})
-        if hidden not in cache:
-            cache[hidden] = _build_tiles_pair(self, hidden)
-        return cache[hidden]
+        if "pair" not in cache:                 # tiles hold 128-column chunks of rows: one layout for every width
+            cache["pair"] = _build_tiles_pair(self, hidden)
+        return cache["pair"]
 
     def to(self, device, non_blocking: bool = False) -> "StationGraph":
         if torch.device(device) == self.device:
@@ -64,6 +66,7 @@ class StationGraph:
         return torch.stack([self.col.long(), rows])[:, inv]
 
 
+TILE_ROW_BYTES = 512       # the kernels stage one 128-column fp32 chunk of a row at a time
 TILED_MIN_ROWS = 16384     # below this the warp-per-row kernels win (too few tiles to fill 148 SMs)
 
 
@@ -71,9 +74,11 @@ class StationTiles:
     """Tile-major layout of one gather matrix for rc_gine_aggr_{fwd,bwd}_tiled (include/rc_b200.h: rc_gine_tiles)."""
     _ARRAYS = ("tile_stage_ptr", "tile_blk_ptr", "stage_id", "blocks")
 
-    def __init__(self, n_tiles: int, max_staged: int, max_block_bytes: int, row_bytes: int, num_rows: int, arrays: dict):
+    def __init__(self, n_tiles: int, max_staged: int, max_block_bytes: int, row_bytes: int, num_rows: int, arrays: dict,
+                 n_entries: int = 0):
         self.n_tiles, self.max_staged, self.max_block_bytes, self.row_bytes = n_tiles, max_staged, max_block_bytes, row_bytes
         self.num_rows = num_rows
+        self.n_entries = n_entries          # shared-memory row reads per pass (edges / n_entries = reuse factor)
         self.arrays = arrays
         self.struct = _lib.rc_gine_tiles(n_tiles, max_staged, max_block_bytes, row_bytes,
                                          *[arrays[a].data_ptr() for a in self._ARRAYS])
@@ -89,7 +94,18 @@ class StationTiles:
 
     def to(self, device) -> "StationTiles":
         return StationTiles(self.n_tiles, self.max_staged, self.max_block_bytes, self.row_bytes, self.num_rows,
-                            {k: v.to(device) for k, v in self.arrays.items()})
+                            {k: v.to(device) for k, v in self.arrays.items()}, self.n_entries)
+
+    def verify(self, rowptr: torch.Tensor, col: torch.Tensor, attr: torch.Tensor) -> None:
+        """rc_gine_tiles_verify_host: raises RcError unless the tiles hold exactly the edges of the CSR."""
+        rowptr, col, attr = (t.detach().cpu().contiguous() for t in (rowptr, col, attr))
+        a = {k: v.cpu().contiguous() for k, v in self.arrays.items()}
+        e = col.numel()
+        if e == 0:
+            col, attr = torch.zeros(1, dtype=torch.int32), torch.zeros(1)
+        _lib.check(_lib.lib().rc_gine_tiles_verify_host(
+            rowptr.data_ptr(), col.data_ptr(), attr.data_ptr(), rowptr.numel() - 1, e, self.n_tiles, self.max_staged,
+            self.max_block_bytes, self.row_bytes, *[a[k].data_ptr() for k in self._ARRAYS]), "rc_gine_tiles_verify_host")
 
 
 def tile_limits(hidden: int):
@@ -111,17 +127,18 @@ def build_tiles_host(rowptr: torch.Tensor, col: torch.Tensor, attr: torch.Tensor
     tsp = torch.zeros(n + 1, dtype=torch.int32)
     tbp = torch.zeros(n + 1, dtype=torch.int32)
     stage = torch.empty(max(n + e, 1), dtype=torch.int32)
-    blocks = torch.empty(max(10 * n + 2 * e, 4), dtype=torch.int32)
+    blocks = torch.empty(max(16 * n + 4 * e, 4), dtype=torch.int32)
     nt, ms, mb = C.c_int32(), C.c_int32(), C.c_int32()
-    ns, nu = C.c_int64(), C.c_int64()
+    ns, nu, ne = C.c_int64(), C.c_int64(), C.c_int64()
     _lib.check(L.rc_gine_tiles_build_host(rowptr.data_ptr(), col.data_ptr(), attr.data_ptr(), n, e, int(max_src),
                                           int(max_block_bytes), int(row_bytes), tsp.data_ptr(), tbp.data_ptr(),
                                           stage.data_ptr(), blocks.data_ptr(), C.addressof(nt), C.addressof(ns),
-                                          C.addressof(nu), C.addressof(ms), C.addressof(mb)), "rc_gine_tiles_build_host")
+                                          C.addressof(nu), C.addressof(ms), C.addressof(mb), C.addressof(ne)),
+               "rc_gine_tiles_build_host")
     arrays = {"tile_stage_ptr": tsp[:nt.value + 1].clone(), "tile_blk_ptr": tbp[:nt.value + 1].clone(),
               "stage_id": stage[:ns.value].clone() if ns.value else torch.zeros(1, dtype=torch.int32)[:0],
               "blocks": blocks[:max(4 * nu.value, 4)].clone()}
-    return StationTiles(nt.value, ms.value, mb.value, int(row_bytes), n, arrays)
+    return StationTiles(nt.value, ms.value, mb.value, int(row_bytes), n, arrays, ne.value)
 
 
 def _build_tiles_pair(g: "StationGraph", hidden: int):
@@ -129,8 +146,8 @@ def _build_tiles_pair(g: "StationGraph", hidden: int):
     if lim is None or g.num_nodes < TILED_MIN_ROWS:
         return None
     try:
-        fwd = build_tiles_host(g.rowptr, g.col, g.attr, lim[0], lim[1], 4 * hidden)
-        bwd = build_tiles_host(g.t_rowptr, g.t_dst, g.t_attr, lim[0], lim[1], 4 * hidden)
+        fwd = build_tiles_host(g.rowptr, g.col, g.attr, lim[0], lim[1], TILE_ROW_BYTES)
+        bwd = build_tiles_host(g.t_rowptr, g.t_dst, g.t_attr, lim[0], lim[1], TILE_ROW_BYTES)
     except _lib.RcError:
         return None            # some row gathers more rows than one CTA can stage: the untiled kernels handle it
     return fwd.to(g.device), bwd.to(g.device)

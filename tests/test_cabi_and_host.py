@@ -149,31 +149,48 @@ def test_model_state_dict_layout_and_ctor_errors(golden_model):
 
 # ------------------------------------------------------------------------------------------------ station tiles
 def _check_tiles(sg_rowptr, sg_col, sg_attr, tiles, max_src, max_block, row_bytes=512):
-    """Invariants of rc_gine_tiles_build_host: a partition of the rows, at most max_src staged rows and max_block
-    record bytes per tile, and every row's edges recoverable in CSR slot order with bit-identical attributes."""
+    """Invariants of rc_gine_tiles_build_host, decoded here independently of rc_gine_tiles_verify_host: a partition of
+    the rows into groups of at most three, at most max_src staged rows and max_block record bytes per tile, and every
+    row's edges recoverable from its group's entries with bit-identical attributes."""
+    tiles.verify(torch.from_numpy(sg_rowptr), torch.from_numpy(sg_col), torch.from_numpy(sg_attr))
     a = {k: v.numpy() for k, v in tiles.arrays.items()}
     n = len(sg_rowptr) - 1
     tsp, tbp, stage = a["tile_stage_ptr"], a["tile_blk_ptr"], a["stage_id"]
     blocks = a["blocks"].reshape(-1, 4)
     assert len(tsp) == tiles.n_tiles + 1 and tsp[0] == 0 and tsp[-1] == len(stage) and tbp[0] == 0
-    owned, staged_max, blk_max, edges = [], 0, 0, 0
+    owned, staged_max, blk_max, edges, entries = [], 0, 0, 0, 0
     for t in range(tiles.n_tiles):
         blk = blocks[tbp[t]:tbp[t + 1]]
-        nrows, nst, ne, _ = blk[0]
+        nrows, nst, ngroups, ne = blk[0]
         staged = stage[tsp[t]:tsp[t + 1]]
         assert nst == len(staged) <= max_src and len(np.unique(staged)) == nst and 16 * len(blk) <= max_block
         staged_max, blk_max, edges = max(staged_max, nst), max(blk_max, 16 * len(blk)), edges + ne
-        words = blk.reshape(-1)
-        for r in range(nrows):
-            v, eoff, deg, _ = blk[1 + r]
-            assert v == staged[r] and eoff % 16 == 0          # own rows lead the stage list, in tile order
-            owned.append(v)
-            meta = words[eoff // 4: eoff // 4 + 2 * deg].reshape(-1, 2)
-            assert (meta[:, 0] % row_bytes == 0).all()
-            assert np.array_equal(staged[meta[:, 0] // row_bytes], sg_col[sg_rowptr[v]:sg_rowptr[v + 1]])
-            assert np.array_equal(meta[:, 1].view(np.uint32), sg_attr[sg_rowptr[v]:sg_rowptr[v + 1]].view(np.uint32))
+        r = 0
+        for g in range(ngroups):
+            u0, u1, u2 = blk[1 + 3 * g: 4 + 3 * g]
+            cnt = [0, u1[0] & 0xffff, (u1[0] >> 16) & 0xffff, u1[1] & 0xffff, (u1[1] >> 16) & 0xffff, u1[2] & 0xffff,
+                   (u1[2] >> 16) & 0xffff, u1[3]]
+            assert u0[3] % 16 == 0 and u2[3] == r * row_bytes       # own rows lead the stage list, group by group
+            ent = blk[u0[3] // 16: u0[3] // 16 + sum(cnt)]
+            entries += len(ent)
+            cls = np.repeat(np.arange(8), cnt)
+            assert (ent[:, 0] % row_bytes == 0).all()
+            for k in range(3):
+                v = u0[k]
+                if v < 0:
+                    assert (u0[k:3] < 0).all() and not (cls & (1 << k)).any()
+                    continue
+                assert v == staged[r] and u2[k:k + 1].view(np.float32)[0] == sg_rowptr[v + 1] - sg_rowptr[v]
+                r += 1
+                owned.append(v)
+                use = (cls & (1 << k)) != 0
+                got = sorted(zip(staged[ent[use, 0] // row_bytes].tolist(), ent[use, 1 + k].view(np.uint32).tolist()))
+                want = sorted(zip(sg_col[sg_rowptr[v]:sg_rowptr[v + 1]].tolist(),
+                                  sg_attr[sg_rowptr[v]:sg_rowptr[v + 1]].view(np.uint32).tolist()))
+                assert got == want
+        assert r == nrows
     assert np.array_equal(np.sort(np.array(owned, dtype=np.int64)), np.arange(n))
-    assert edges == len(sg_col)
+    assert edges == len(sg_col) and entries == tiles.n_entries
     assert staged_max == tiles.max_staged and blk_max == tiles.max_block_bytes
 
 
@@ -184,7 +201,7 @@ def test_station_tiles_batched_reference_graph(golden_graph):
     ei_b, ea_b = og.collate_edges(ei, ea, 122, batch)
     sg = G.build_station_graph(torch.from_numpy(ei_b), torch.from_numpy(ea_b), 122 * batch)
     max_src, max_block = G.tile_limits(128)
-    assert max_src * 512 + max_block + 16 <= 227 * 512 - 1024 and max_src >= 160
+    assert 2 * (max_src * 512 + max_block) + 64 <= 227 * 1024 and max_src >= 160      # two buffers + control block
     for rp, col, attr in ((sg.rowptr, sg.col, sg.attr), (sg.t_rowptr, sg.t_dst, sg.t_attr)):
         tiles = G.build_tiles_host(rp, col, attr, max_src, max_block, 512)
         _check_tiles(rp.numpy(), col.numpy(), attr.numpy(), tiles, max_src, max_block)
@@ -216,12 +233,13 @@ def test_station_tiles_edge_cases():
     with pytest.raises(_lib.RcError):
         G.build_tiles_host(sg.rowptr, sg.col, sg.attr, 2, 4096, 512)
     star = G.build_station_graph(torch.tensor([[1, 2, 3, 4, 5], [0, 0, 0, 0, 0]]), torch.ones(5), 6)
-    with pytest.raises(_lib.RcError):          # header 16 + row record 16 + 3 edge records 48 = 80 bytes > 64
-        G.build_tiles_host(star.rowptr, star.col, star.attr, 100, 64, 512)
+    # the hub's group: header 16 + group record 48 + 6 entries (5 leaves + the hub's own row) 96 = 160 bytes
+    with pytest.raises(_lib.RcError):
+        G.build_tiles_host(star.rowptr, star.col, star.attr, 100, 128, 512)
     _check_tiles(star.rowptr.numpy(), star.col.numpy(), star.attr.numpy(),
-                 G.build_tiles_host(star.rowptr, star.col, star.attr, 100, 80, 512), 100, 80)
+                 G.build_tiles_host(star.rowptr, star.col, star.attr, 100, 256, 512), 100, 256)
     # empty graph
     empty = G.build_station_graph(torch.zeros((2, 0), dtype=torch.int64), torch.zeros(0), 0)
     tiles = G.build_tiles_host(empty.rowptr, empty.col, empty.attr, 8, 4096, 512)
     assert tiles.n_tiles == 0 and tiles.n_staged == 0
-    assert G.tile_limits(100) is None and G.tile_limits(512)[0] >= 80
+    assert G.tile_limits(100) is None and G.tile_limits(512) == G.tile_limits(128)

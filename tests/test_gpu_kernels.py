@@ -419,8 +419,8 @@ def test_deepsets_tensor_core_path_bf16(dev, m, em, f, h):
 
 # ------------------------------------------------------------------------------------------------ station tiles
 def _tiled_vs_untiled(dev, sg, m, h, seed, want=None):
-    """Runs both aggregation paths on the same inputs; h and dx must agree bit for bit (same expressions, same
-    summation order), the parameter gradients to rounding (different partial-sum grouping)."""
+    """Runs both aggregation paths on the same inputs; they agree to rounding (the tiled kernels sum class by class and
+    add the edge bias once per row, the parameter gradients group their partial sums differently)."""
     from raincast_gnn_b200 import kernels as K
     g = torch.Generator().manual_seed(seed)
     x, gout, add = (torch.randn(m, h, generator=g).to(dev) for _ in range(3))
@@ -437,10 +437,18 @@ def _tiled_vs_untiled(dev, sg, m, h, seed, want=None):
                                                      torch.cuda.current_stream().cuda_stream))
         outs[tiled] = (hh, dx, dw, db, de)
     torch.cuda.synchronize()
-    assert torch.equal(outs[True][0], outs[False][0]), "tiled forward differs from the warp-per-row kernel"
-    assert torch.equal(outs[True][1], outs[False][1]), "tiled backward dx differs from the warp-per-row kernel"
-    for i in (2, 3, 4):
-        assert rel_err(_np(outs[True][i]), _np(outs[False][i])) < TOL
+    assert rel_err(_np(outs[True][0]), _np(outs[False][0])) < 2e-6, "tiled forward differs from the warp-per-row kernel"
+    # the two kernels round x_j + a w + b differently (x_j + (a w + b) > 0 vs x_j + a w > -b): a unit within one
+    # rounding of its ReLU threshold - a few in 1e8 evaluations - can land on either side and moves one element of dx
+    # by g; everything else agrees to rounding
+    a, b = _np(outs[True][1]), _np(outs[False][1])
+    off = np.abs(a - b) > 2e-6 * np.abs(b).max()
+    assert off.sum() <= max(2, 1e-5 * off.size), "tiled backward dx differs from the warp-per-row kernel"
+    # each such unit also moves d w_edge by g * a and d b_edge by g
+    flip = float(off.sum()) * float(gout.abs().max()) * max(1.0, float(sg.attr.abs().max()))
+    for i in (2, 3):
+        assert rel_err(_np(outs[True][i]), _np(outs[False][i])) < TOL + flip / float(outs[False][i].abs().max())
+    assert rel_err(_np(outs[True][4]), _np(outs[False][4])) < TOL
     return outs[True]
 
 
@@ -451,7 +459,7 @@ def _lib_mod():
 
 @pytest.mark.parametrize("h", [128, 256, 512])
 def test_gine_tiled_radius_graph(dev, h):
-    """Station tiles on a 20k-node radius graph (mean degree 20): bitwise equal to the untiled kernels, and within
+    """Station tiles on a 20k-node radius graph (mean degree 20): equal to the untiled kernels to rounding, and within
     1e-5 of the float64 restatement of PyG's GINEConv on dyadic inputs (no unit near its ReLU threshold)."""
     from raincast_gnn_b200 import graph as G, kernels as K
     from raincast_gnn_b200.utils import synthetic as syn
@@ -499,3 +507,26 @@ def test_gine_tiled_batched_reference_graphs(dev, golden_graph):
     tiles = sg.tiles(128)
     assert tiles is not None and tiles[0].n_tiles == batch and tiles[0].n_halo == 0 and tiles[1].n_halo == 0
     _tiled_vs_untiled(dev, sg, m, 128, seed=7)
+
+
+@pytest.mark.parametrize("h,max_src,max_block", [(128, 48, 4096), (256, 64, 1 << 16), (384, 100, 2048)])
+def test_gine_tiled_irregular_multigraph(dev, h, max_src, max_block):
+    """Tiles forced onto a small asymmetric multigraph (repeated edges, random self loops, rows without edges, small
+    staging / block limits so that tiles split and give rows back): same results as the warp-per-row kernels."""
+    from raincast_gnn_b200 import graph as G
+    g = torch.Generator().manual_seed(h)
+    m, e = 900, 9000
+    src = torch.randint(0, m - 50, (e,), generator=g)                   # the last 50 nodes gather and feed nothing
+    dst = (src + torch.randint(-12, 13, (e,), generator=g)).clamp_(0, m - 51)
+    ei = torch.stack([src, dst])
+    ei = torch.cat([ei, ei[:, :300]], dim=1)                            # 300 repeated (src, dst) pairs, other attributes
+    ea = torch.rand(ei.shape[1], 1, generator=g) * 4.0 - 1.0
+    sg = G.build_station_graph(ei, ea, m)
+    fwd = G.build_tiles_host(sg.rowptr, sg.col, sg.attr, max_src, max_block, G.TILE_ROW_BYTES)
+    bwd = G.build_tiles_host(sg.t_rowptr, sg.t_dst, sg.t_attr, max_src, max_block, G.TILE_ROW_BYTES)
+    fwd.verify(sg.rowptr, sg.col, sg.attr)
+    bwd.verify(sg.t_rowptr, sg.t_dst, sg.t_attr)
+    assert fwd.n_tiles > 8 and fwd.n_entries < ei.shape[1]
+    sg = sg.to(dev)
+    sg.__dict__["_tiles"] = {"pair": (fwd.to(dev), bwd.to(dev))}
+    _tiled_vs_untiled(dev, sg, m, h, seed=3 * h)

@@ -32,7 +32,8 @@ def run(name, ei, ea, n):
     tiles = sg.tiles(h)
     t2 = time.time()
     print(f"== {name}: {n} nodes, {e} edges; csr build {t1-t0:.2f}s, tiles build {t2-t1:.2f}s: "
-          f"fwd {tiles[0].n_tiles} tiles, halo {tiles[0].n_halo} ({(tiles[0].n_halo + n) / n:.2f} staged rows/row), max staged {tiles[0].max_staged}, max block {tiles[0].max_block_bytes} B", flush=True)
+          f"fwd {tiles[0].n_tiles} tiles, halo {tiles[0].n_halo} ({(tiles[0].n_halo + n) / n:.2f} staged rows/row), max staged {tiles[0].max_staged}, max block {tiles[0].max_block_bytes} B, "
+          f"{e / max(tiles[0].n_entries, 1):.2f} edges per shared-memory row read", flush=True)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(n, h, generator=g).to(dev); gout = torch.randn(n, h, generator=g).to(dev)
     w, b, eps = torch.randn(h, generator=g).to(dev), torch.randn(h, generator=g).to(dev), torch.zeros(1, device=dev)
