@@ -30,10 +30,24 @@ namespace rc {
 
 constexpr int kSmemPerCTA = 227 * 1024;   // opt-in maximum of dynamic shared memory
 constexpr int kTileRowBytes = 512;        // one 128-column chunk of a row
-constexpr int kProdWarps = 4;             // producer warps: warp w runs on sub-partition w
-constexpr int kFwdThreads = 1024;
-constexpr int kBwdThreads = 768;
+#ifndef RC_PROD_WARPS
+#define RC_PROD_WARPS 8
+#endif
+#ifndef RC_FWD_THREADS
+#define RC_FWD_THREADS 1024
+#endif
+#ifndef RC_BWD_THREADS
+#define RC_BWD_THREADS 768
+#endif
+constexpr int kProdWarps = RC_PROD_WARPS;  // producer warps: warp w runs on sub-partition w % 4
+static_assert(32 * kProdWarps * 512 >= 227 * 1024 / 2, "one staged row per producer lane");
+constexpr int kFwdThreads = RC_FWD_THREADS;
+constexpr int kBwdThreads = RC_BWD_THREADS;
 constexpr int kCtrlBytes = 64;            // full[2], empty[2] mbarriers + two item counters
+
+// scale factors of the saturating-FMA ReLU (see relu_acc / masked_acc)
+constexpr float kDown = 5.421010862427522e-20f;   // 2^-64
+constexpr float kUp = 18446744073709551616.0f;    // 2^64
 
 struct TilesP {
   int n_tiles;
@@ -62,56 +76,84 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_arrive_on_copies(unsigned long long* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, int parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// waiting warps back off: a spinning warp takes issue slots from the warps it is waiting for
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+  while (!mbar_test(bar, parity)) __nanosleep(64);
 }
 
 // Producer warps: stage this CTA's tiles, two in flight.  `src` already points at the CTA's column chunk; rows are
-// `row_stride` bytes apart in global memory and 512 bytes apart in shared memory.
+// `row_stride` bytes apart in global memory and 512 bytes apart in shared memory.  Lane l of warp w owns staged row
+// w + l * kProdWarps of every tile (32 * kProdWarps >= the most rows a buffer can hold): the tile's ranges and the
+// lane's row id are fetched BEFORE waiting for the buffer, so that a released buffer is refilled without a trip to
+// global memory first.
+template <bool BIAS>
 __device__ __forceinline__ void produce_tiles(const float* __restrict__ src, size_t row_stride, const TilesP& t, int first, int step,
-                                              unsigned char* smem, Ctrl* ctrl, int lane, int warp) {
-  const unsigned char* base = reinterpret_cast<const unsigned char*>(src) + 16 * lane;
+                                              unsigned char* smem, Ctrl* ctrl, int lane, int warp,
+                                              float4 bias = make_float4(0.f, 0.f, 0.f, 0.f)) {
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(src);
+  const int mine = warp + lane * kProdWarps;
   int it = 0;
+  // ranges and row id of the first tile; those of tile i + 1 are fetched while the copies of tile i are in flight
+  int s0 = 0, nst = 0, b0 = 0, bunits = 0, my_id = 0;
+  if (first < t.n_tiles) {
+    s0 = __ldg(t.tile_stage_ptr + first); nst = __ldg(t.tile_stage_ptr + first + 1) - s0;
+    b0 = __ldg(t.tile_blk_ptr + first); bunits = __ldg(t.tile_blk_ptr + first + 1) - b0;
+    my_id = mine < nst ? __ldg(t.stage_id + s0 + mine) : 0;
+  }
   for (int tile = first; tile < t.n_tiles; tile += step, ++it) {
     const int b = it & 1;
     unsigned char* rows = smem + (size_t)b * t.buf_bytes;
     unsigned char* blk = rows + t.rows_bytes;
+    const unsigned char* my_src = base + (size_t)my_id * row_stride;   // start of this lane's row
     if (it >= 2) mbar_wait(&ctrl->empty[b], ((it >> 1) & 1) ^ 1);      // every consumer warp is done with this buffer
-    const int s0 = __ldg(t.tile_stage_ptr + tile), nst = __ldg(t.tile_stage_ptr + tile + 1) - s0;
-    const int b0 = __ldg(t.tile_blk_ptr + tile), bunits = __ldg(t.tile_blk_ptr + tile + 1) - b0;
+    // gathered rows: the row addresses are broadcast lane by lane; every lane copies 16 bytes of every row of the warp
+    const int cnt = nst > warp ? (nst - warp + kProdWarps - 1) / kProdWarps : 0;
+    unsigned char* dst0 = rows + (size_t)warp * kTileRowBytes + 16 * lane;
+    for (int k = 0; k < cnt; ++k) {
+      const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)my_src, k) + 16 * lane;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst0 + k * (kProdWarps * kTileRowBytes))), "l"(sp) : "memory");
+    }
     // the tile's block of group / entry records: contiguous, 16 bytes per thread per pass
     const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.blocks) + (size_t)b0 * 16;
     for (int u = warp * 32 + lane; u < bunits; u += 32 * kProdWarps)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(blk + 16 * u)), "l"(bsrc + 16 * (size_t)u) : "memory");
-    // gathered rows: lane k of a warp fetches the id of the warp's k-th row, then the ids are broadcast row by row
-    for (int l0 = warp; l0 < nst; l0 += 32 * kProdWarps) {
-      const int mine = l0 + lane * kProdWarps;
-      const int my_id = mine < nst ? __ldg(t.stage_id + s0 + mine) : 0;
-      const int cnt = min(32, (nst - l0 + kProdWarps - 1) / kProdWarps);
+    const int next = tile + step;
+    if (next < t.n_tiles) {
+      s0 = __ldg(t.tile_stage_ptr + next); nst = __ldg(t.tile_stage_ptr + next + 1) - s0;
+      b0 = __ldg(t.tile_blk_ptr + next); bunits = __ldg(t.tile_blk_ptr + next + 1) - b0;
+      my_id = mine < nst ? __ldg(t.stage_id + s0 + mine) : 0;
+    }
+    if (warp == 0 && lane == 0) ctrl->counter[b] = 0;   // nobody claims from this buffer between its release and the arrivals below
+    if (BIAS) {
+      // every lane rewrites the 16 bytes it copied itself (no other thread involved): x_j -> (x_j + b) * 2^-64
+      asm volatile("cp.async.wait_all;" ::: "memory");
       for (int k = 0; k < cnt; ++k) {
-        const int id = __shfl_sync(0xffffffffu, my_id, k);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(rows + (size_t)(l0 + k * kProdWarps) * kTileRowBytes + 16 * lane)),
-                     "l"(base + (size_t)id * row_stride) : "memory");
+        float4* p = reinterpret_cast<float4*>(dst0 + k * (kProdWarps * kTileRowBytes));
+        float4 v = *p;
+        v.x = fmaf(v.x, kDown, bias.x); v.y = fmaf(v.y, kDown, bias.y);
+        v.z = fmaf(v.z, kDown, bias.z); v.w = fmaf(v.w, kDown, bias.w);
+        *p = v;
       }
+      mbar_arrive(&ctrl->full[b]);          // release: the rows, the records and the counter are visible to whoever sees the phase
+    } else {
+      if (warp == 0 && lane == 0) mbar_arrive(&ctrl->full[b]);    // release: orders the counter store before the consumers' claims
+      mbar_arrive_on_copies(&ctrl->full[b]);
     }
-    if (warp == 0 && lane == 0) {
-      ctrl->counter[b] = 0;                 // nobody claims from this buffer between its release and the arrival below
-      mbar_arrive(&ctrl->full[b]);          // release: orders the counter store before the consumers' claims
-    }
-    mbar_arrive_on_copies(&ctrl->full[b]);
   }
 }
 
-__device__ __forceinline__ void init_ctrl(Ctrl* ctrl, int consumer_warps) {
+__device__ __forceinline__ void init_ctrl(Ctrl* ctrl, int consumer_warps, int producer_arrivals) {
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&ctrl->full[b], 32 * kProdWarps + 1);
+      mbar_init(&ctrl->full[b], producer_arrivals);
       mbar_init(&ctrl->empty[b], consumer_warps);
       ctrl->counter[b] = 0;
     }
@@ -129,37 +171,47 @@ __device__ __forceinline__ int claim_item(int* next_item, int lane) {
 __device__ __forceinline__ float4 lds4(const unsigned char* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ int4 ldsi4(const unsigned char* p) { return *reinterpret_cast<const int4*>(p); }
 
-// acc += max(a * w + v, nb)   (nb = -b_edge; the row adds degree * b_edge at the end)
-__device__ __forceinline__ void relu_acc(float4& acc, float4 v, float a, float4 w, float4 nb) {
-  const float2 a2 = make_float2(a, a);
-  float2 z0 = __ffma2_rn(a2, make_float2(w.x, w.y), make_float2(v.x, v.y));
-  float2 z1 = __ffma2_rn(a2, make_float2(w.z, w.w), make_float2(v.z, v.w));
-  z0.x = fmaxf(z0.x, nb.x); z0.y = fmaxf(z0.y, nb.y);
-  z1.x = fmaxf(z1.x, nb.z); z1.y = fmaxf(z1.y, nb.w);
+// The ReLU rides on the FMA: fma.rn.sat clamps its result to [0, 1], so with the operands scaled by kDown = 2^-64
+// (exact: a power of two) sat(a * (w kDown) + (x_j + b) kDown) = kDown * relu(x_j + a w + b) for every message below
+// 2^64.  Measured on B200 (tools/ubench/pipes.cu): 2 FFMA.SAT + FADD2 per two columns cost 4.7 issue cycles per
+// sub-partition against 7.3 for FFMA2 + 2 FMNMX + FADD2 - FMNMX runs at half rate and does not overlap the FMA pipe.
+// (A NaN input gives 0 here, NaN in the reference.)
+
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float d;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// acc += sat(a * ws + vs)   (ws = w kDown, vs = (x_j + b) kDown: staged that way by the producer warps)
+__device__ __forceinline__ void relu_acc(float4& acc, float4 vs, float a, float4 ws) {
+  const float2 z0 = make_float2(fma_sat(a, ws.x, vs.x), fma_sat(a, ws.y, vs.y));
+  const float2 z1 = make_float2(fma_sat(a, ws.z, vs.z), fma_sat(a, ws.w, vs.w));
   const float2 s0 = __fadd2_rn(make_float2(acc.x, acc.y), z0), s1 = __fadd2_rn(make_float2(acc.z, acc.w), z1);
   acc = make_float4(s0.x, s0.y, s1.x, s1.y);
 }
 
 template <int MASK>
-__device__ __forceinline__ void fwd_apply(float4 (&acc)[3], float4 v, int4 rec, float4 w, float4 nb) {
-  if (MASK & 1) relu_acc(acc[0], v, __int_as_float(rec.y), w, nb);
-  if (MASK & 2) relu_acc(acc[1], v, __int_as_float(rec.z), w, nb);
-  if (MASK & 4) relu_acc(acc[2], v, __int_as_float(rec.w), w, nb);
+__device__ __forceinline__ void fwd_apply(float4 (&acc)[3], float4 v, int4 rec, float4 w) {
+  if (MASK & 1) relu_acc(acc[0], v, __int_as_float(rec.y), w);
+  if (MASK & 2) relu_acc(acc[1], v, __int_as_float(rec.z), w);
+  if (MASK & 4) relu_acc(acc[2], v, __int_as_float(rec.w), w);
 }
 
 // the n entries of one class, two in flight; returns the next class's first entry
 template <int MASK>
 __device__ __forceinline__ const unsigned char* fwd_class(float4 (&acc)[3], const unsigned char* p, int n, const unsigned char* rl,
-                                                          float4 w, float4 nb) {
+                                                          float4 w) {
+#pragma unroll 1
   for (; n >= 2; n -= 2, p += 32) {
     const int4 r0 = ldsi4(p), r1 = ldsi4(p + 16);
     const float4 v0 = lds4(rl + r0.x), v1 = lds4(rl + r1.x);
-    fwd_apply<MASK>(acc, v0, r0, w, nb);
-    fwd_apply<MASK>(acc, v1, r1, w, nb);
+    fwd_apply<MASK>(acc, v0, r0, w);
+    fwd_apply<MASK>(acc, v1, r1, w);
   }
   if (n) {
     const int4 r0 = ldsi4(p);
-    fwd_apply<MASK>(acc, lds4(rl + r0.x), r0, w, nb);
+    fwd_apply<MASK>(acc, lds4(rl + r0.x), r0, w);
     p += 16;
   }
   return p;
@@ -174,14 +226,17 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 2 * (size_t)t.buf_bytes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x % chunks, first = blockIdx.x / chunks, step = gridDim.x / chunks;
-  init_ctrl(ctrl, kFwdThreads / 32 - kProdWarps);
+  init_ctrl(ctrl, kFwdThreads / 32 - kProdWarps, 32 * kProdWarps);
+  const float4 w = ldg4(w_edge + 4 * lane + 128 * c), b = ldg4(b_edge + 4 * lane + 128 * c);
   if (warp < kProdWarps) {
-    produce_tiles(x + 128 * c, (size_t)hidden * 4, t, first, step, smem, ctrl, lane, warp);
+    // the staged rows become (x_j + b_edge) * 2^-64
+    produce_tiles<true>(x + 128 * c, (size_t)hidden * 4, t, first, step, smem, ctrl, lane, warp,
+                        make_float4(b.x * kDown, b.y * kDown, b.z * kDown, b.w * kDown));
     return;
   }
   const float self_scale = 1.0f + __ldg(eps_ptr);
-  const float4 w = ldg4(w_edge + 4 * lane + 128 * c), b = ldg4(b_edge + 4 * lane + 128 * c);
-  const float4 nb = make_float4(-b.x, -b.y, -b.z, -b.w);
+  const float4 ws = make_float4(w.x * kDown, w.y * kDown, w.z * kDown, w.w * kDown);
+  const float* xc = x + 128 * c + 4 * lane;
   float* hc = h + 128 * c + 4 * lane;
   int it = 0;
   for (int tile = first; tile < t.n_tiles; tile += step, ++it) {
@@ -195,30 +250,28 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
     // of each other whatever the degree distribution
     for (int grp = claim_item(&ctrl->counter[bf], lane); grp < n_items; grp = claim_item(&ctrl->counter[bf], lane)) {
       const unsigned char* gp = blk + 16 + 48 * grp;
-      const int4 u0 = ldsi4(gp), u1 = ldsi4(gp + 16), u2 = ldsi4(gp + 32);
+      const int4 u0 = ldsi4(gp), u1 = ldsi4(gp + 16);
       float4 acc[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       const unsigned char* p = blk + u0.w;
-      p = fwd_class<1>(acc, p, u1.x & 0xffff, rl, w, nb);
-      p = fwd_class<2>(acc, p, (unsigned)u1.x >> 16, rl, w, nb);
-      p = fwd_class<3>(acc, p, u1.y & 0xffff, rl, w, nb);
-      p = fwd_class<4>(acc, p, (unsigned)u1.y >> 16, rl, w, nb);
-      p = fwd_class<5>(acc, p, u1.z & 0xffff, rl, w, nb);
-      p = fwd_class<6>(acc, p, (unsigned)u1.z >> 16, rl, w, nb);
-      p = fwd_class<7>(acc, p, u1.w, rl, w, nb);
+      p = fwd_class<1>(acc, p, u1.x & 0xffff, rl, ws);
+      p = fwd_class<2>(acc, p, (unsigned)u1.x >> 16, rl, ws);
+      p = fwd_class<3>(acc, p, u1.y & 0xffff, rl, ws);
+      p = fwd_class<4>(acc, p, (unsigned)u1.y >> 16, rl, ws);
+      p = fwd_class<5>(acc, p, u1.z & 0xffff, rl, ws);
+      p = fwd_class<6>(acc, p, (unsigned)u1.z >> 16, rl, ws);
+      p = fwd_class<7>(acc, p, u1.w, rl, ws);
       const int node[3] = {u0.x, u0.y, u0.z};
-      const float deg[3] = {__int_as_float(u2.x), __int_as_float(u2.y), __int_as_float(u2.z)};
-      const unsigned char* self = rl + u2.w;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (node[k] < 0) break;                      // rows of a group are packed to the front
-        const float4 xi = lds4(self + k * kTileRowBytes);
+        const float4 xi = ldg4(xc + (size_t)node[k] * hidden);      // the staged copy carries the bias: x_i comes from L2
         float4 o;
-        o.x = fmaf(self_scale, xi.x, fmaf(deg[k], b.x, acc[k].x));
-        o.y = fmaf(self_scale, xi.y, fmaf(deg[k], b.y, acc[k].y));
-        o.z = fmaf(self_scale, xi.z, fmaf(deg[k], b.z, acc[k].z));
-        o.w = fmaf(self_scale, xi.w, fmaf(deg[k], b.w, acc[k].w));
+        o.x = fmaf(self_scale, xi.x, acc[k].x * kUp);
+        o.y = fmaf(self_scale, xi.y, acc[k].y * kUp);
+        o.z = fmaf(self_scale, xi.z, acc[k].z * kUp);
+        o.w = fmaf(self_scale, xi.w, acc[k].w * kUp);
         st4(hc + (size_t)node[k] * hidden, o);
       }
     }
@@ -227,44 +280,38 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
   }
 }
 
-// One (entry, row) pair of the backward: m = 1[x_s + a*w + b > 0] as 1.0 / 0.0, acc += g * m, s += a * m
-// (s: the entry's sum_k a_k m_k; the weight gradient takes g * s once per entry)
-__device__ __forceinline__ void masked_acc(float4& acc, float4& s, float4 g, float4 xs, float a, float4 w, float4 nb) {
-  const float2 a2 = make_float2(a, a);
-  const float2 z0 = __ffma2_rn(a2, make_float2(w.x, w.y), make_float2(xs.x, xs.y));
-  const float2 z1 = __ffma2_rn(a2, make_float2(w.z, w.w), make_float2(xs.z, xs.w));
-  const float2 m0 = make_float2(z0.x > nb.x ? 1.f : 0.f, z0.y > nb.y ? 1.f : 0.f);
-  const float2 m1 = make_float2(z1.x > nb.z ? 1.f : 0.f, z1.y > nb.w ? 1.f : 0.f);
-  const float2 c0 = __ffma2_rn(make_float2(g.x, g.y), m0, make_float2(acc.x, acc.y));
-  const float2 c1 = __ffma2_rn(make_float2(g.z, g.w), m1, make_float2(acc.z, acc.w));
-  const float2 t0 = __ffma2_rn(a2, m0, make_float2(s.x, s.y)), t1 = __ffma2_rn(a2, m1, make_float2(s.z, s.w));
-  acc = make_float4(c0.x, c0.y, c1.x, c1.y);
-  s = make_float4(t0.x, t0.y, t1.x, t1.y);
+// One (entry, row) pair of the backward.  The mask 1[x_s + a w + b > 0] comes out of a saturating FMA as 1.0 / 0.0:
+// m = sat((a w + x_s + b) * 2^64) (operands pre-scaled; 0 for every z <= 0, 1 for every z >= 2^-64).  Then
+// acc += g * m and s += a * m (s: the entry's sum_k a_k m_k; the weight gradient takes g * s once per entry).
+// Scalar FMAs on purpose: FFMA2 issues at 2.6 cycles per sub-partition against 1.2 for FFMA (tools/ubench/pipes.cu).
+__device__ __forceinline__ void masked_acc(float4& acc, float4& s, float4 g, float4 xb, float a, float4 wu) {
+  const float m0 = fma_sat(a, wu.x, xb.x), m1 = fma_sat(a, wu.y, xb.y), m2 = fma_sat(a, wu.z, xb.z), m3 = fma_sat(a, wu.w, xb.w);
+  acc.x = fmaf(g.x, m0, acc.x); acc.y = fmaf(g.y, m1, acc.y); acc.z = fmaf(g.z, m2, acc.z); acc.w = fmaf(g.w, m3, acc.w);
+  s.x = fmaf(a, m0, s.x); s.y = fmaf(a, m1, s.y); s.z = fmaf(a, m2, s.z); s.w = fmaf(a, m3, s.w);
 }
 
 template <int MASK>
-__device__ __forceinline__ void bwd_apply(float4 (&acc)[3], float4& dw, const float4 (&xs)[3], float4 g, int4 rec, float4 w, float4 nb) {
+__device__ __forceinline__ void bwd_apply(float4 (&acc)[3], float4& dw, const float4 (&xb)[3], float4 g, int4 rec, float4 wu) {
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (MASK & 1) masked_acc(acc[0], s, g, xs[0], __int_as_float(rec.y), w, nb);
-  if (MASK & 2) masked_acc(acc[1], s, g, xs[1], __int_as_float(rec.z), w, nb);
-  if (MASK & 4) masked_acc(acc[2], s, g, xs[2], __int_as_float(rec.w), w, nb);
-  const float2 d0 = __ffma2_rn(make_float2(g.x, g.y), make_float2(s.x, s.y), make_float2(dw.x, dw.y));
-  const float2 d1 = __ffma2_rn(make_float2(g.z, g.w), make_float2(s.z, s.w), make_float2(dw.z, dw.w));
-  dw = make_float4(d0.x, d0.y, d1.x, d1.y);
+  if (MASK & 1) masked_acc(acc[0], s, g, xb[0], __int_as_float(rec.y), wu);
+  if (MASK & 2) masked_acc(acc[1], s, g, xb[1], __int_as_float(rec.z), wu);
+  if (MASK & 4) masked_acc(acc[2], s, g, xb[2], __int_as_float(rec.w), wu);
+  dw.x = fmaf(g.x, s.x, dw.x); dw.y = fmaf(g.y, s.y, dw.y); dw.z = fmaf(g.z, s.z, dw.z); dw.w = fmaf(g.w, s.w, dw.w);
 }
 
 template <int MASK>
 __device__ __forceinline__ const unsigned char* bwd_class(float4 (&acc)[3], float4& dw, const float4 (&xs)[3], const unsigned char* p,
-                                                          int n, const unsigned char* rl, float4 w, float4 nb) {
+                                                          int n, const unsigned char* rl, float4 w) {
+#pragma unroll 1
   for (; n >= 2; n -= 2, p += 32) {
     const int4 r0 = ldsi4(p), r1 = ldsi4(p + 16);
     const float4 v0 = lds4(rl + r0.x), v1 = lds4(rl + r1.x);
-    bwd_apply<MASK>(acc, dw, xs, v0, r0, w, nb);
-    bwd_apply<MASK>(acc, dw, xs, v1, r1, w, nb);
+    bwd_apply<MASK>(acc, dw, xs, v0, r0, w);
+    bwd_apply<MASK>(acc, dw, xs, v1, r1, w);
   }
   if (n) {
     const int4 r0 = ldsi4(p);
-    bwd_apply<MASK>(acc, dw, xs, lds4(rl + r0.x), r0, w, nb);
+    bwd_apply<MASK>(acc, dw, xs, lds4(rl + r0.x), r0, w);
     p += 16;
   }
   return p;
@@ -282,15 +329,16 @@ gine_aggr_bwd_tiled_kernel(const float* __restrict__ g, const float* __restrict_
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 2 * (size_t)t.buf_bytes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x % chunks, first = blockIdx.x / chunks, step = gridDim.x / chunks;
-  init_ctrl(ctrl, NW - kProdWarps);
+  init_ctrl(ctrl, NW - kProdWarps, 32 * kProdWarps + 1);
   float4 dw = make_float4(0.f, 0.f, 0.f, 0.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
   double deps = 0.0;   // <g, x> cancels heavily over M*H products: float64 across rows
   if (warp < kProdWarps) {
-    produce_tiles(g + 128 * c, (size_t)hidden * 4, t, first, step, smem, ctrl, lane, warp);
+    produce_tiles<false>(g + 128 * c, (size_t)hidden * 4, t, first, step, smem, ctrl, lane, warp);
   } else {
     const float self_scale = 1.0f + __ldg(eps_ptr);
     const float4 w = ldg4(w_edge + 4 * lane + 128 * c), b = ldg4(b_edge + 4 * lane + 128 * c);
-    const float4 nb = make_float4(-b.x, -b.y, -b.z, -b.w);
+    const float4 wu = make_float4(w.x * kUp, w.y * kUp, w.z * kUp, w.w * kUp);
+    const float4 bu = make_float4(b.x * kUp, b.y * kUp, b.z * kUp, b.w * kUp);
     const size_t col0 = 128 * c + 4 * lane;
     int it = 0;
     for (int tile = first; tile < t.n_tiles; tile += step, ++it) {
@@ -304,26 +352,33 @@ gine_aggr_bwd_tiled_kernel(const float* __restrict__ g, const float* __restrict_
         const unsigned char* gp = blk + 16 + 48 * grp;
         const int4 u0 = ldsi4(gp), u1 = ldsi4(gp + 16), u2 = ldsi4(gp + 32);
         const int node[3] = {u0.x, u0.y, u0.z};
-        float4 xs[3], acc[3];
+        const unsigned char* self = rl + u2.w;
+        float4 xs[3], acc[3];       // xs: the row's own (x_s + b) * 2^64 (after its <g_s, x_s> went into d eps)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           xs[k] = node[k] >= 0 ? ldg4(x + (size_t)node[k] * hidden + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (node[k] >= 0) {
+            const float4 gj = lds4(self + k * kTileRowBytes);
+            deps += (double)(gj.x * xs[k].x + gj.y * xs[k].y + gj.z * xs[k].z + gj.w * xs[k].w);
+          }
+          xs[k] = make_float4(fmaf(xs[k].x, kUp, bu.x), fmaf(xs[k].y, kUp, bu.y), fmaf(xs[k].z, kUp, bu.z), fmaf(xs[k].w, kUp, bu.w));
+        }
         const unsigned char* p = blk + u0.w;
-        p = bwd_class<1>(acc, dw, xs, p, u1.x & 0xffff, rl, w, nb);
-        p = bwd_class<2>(acc, dw, xs, p, (unsigned)u1.x >> 16, rl, w, nb);
-        p = bwd_class<3>(acc, dw, xs, p, u1.y & 0xffff, rl, w, nb);
-        p = bwd_class<4>(acc, dw, xs, p, (unsigned)u1.y >> 16, rl, w, nb);
-        p = bwd_class<5>(acc, dw, xs, p, u1.z & 0xffff, rl, w, nb);
-        p = bwd_class<6>(acc, dw, xs, p, (unsigned)u1.z >> 16, rl, w, nb);
-        p = bwd_class<7>(acc, dw, xs, p, u1.w, rl, w, nb);
-        const unsigned char* self = rl + u2.w;
+        p = bwd_class<1>(acc, dw, xs, p, u1.x & 0xffff, rl, wu);
+        p = bwd_class<2>(acc, dw, xs, p, (unsigned)u1.x >> 16, rl, wu);
+        p = bwd_class<3>(acc, dw, xs, p, u1.y & 0xffff, rl, wu);
+        p = bwd_class<4>(acc, dw, xs, p, (unsigned)u1.y >> 16, rl, wu);
+        p = bwd_class<5>(acc, dw, xs, p, u1.z & 0xffff, rl, wu);
+        p = bwd_class<6>(acc, dw, xs, p, (unsigned)u1.z >> 16, rl, wu);
+        p = bwd_class<7>(acc, dw, xs, p, u1.w, rl, wu);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           if (node[k] < 0) break;
           const float4 gj = lds4(self + k * kTileRowBytes);
-          deps += (double)(gj.x * xs[k].x + gj.y * xs[k].y + gj.z * xs[k].z + gj.w * xs[k].w);
           // sum_e gm_e = acc: the bias gradient takes it once per row
           db.x += acc[k].x; db.y += acc[k].y; db.z += acc[k].z; db.w += acc[k].w;
           float4 o;
