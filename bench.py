@@ -9,8 +9,9 @@ reference shape (122 stations x 11 members x 35 features, H=128, 4 GINE layers, 
 fp32): forward, CRPS, backward, gradient all-reduce (N > 1), AdamW.  Prints ONE JSON line on rank 0.
 
   value  — whole-job graphs/s with the batch already resident in HBM (CUDA-event time of the K steps)
-  e2e    — the same through the public engine call with HOST (pinned) batches: H2D of x / ensemble / y and a
-           D2H read of the loss inside every timed step
+  e2e    — the same through the public engine calls with HOST (pinned) batches: inside every timed step one H2D
+           copy of x / ensemble / y (the next step's batch, prefetched on a copy stream while this step runs, as
+           train.py does) and a D2H read of the loss
   roofline — the GINE aggregation forward kernel on the config-4 graph (100k nodes, 2 978 560 edges,
            H=128): algorithmic bytes 2*M*H*4 + E*8 + (M+1)*4 + 8*H   / mean CUDA-event time
   cpu_baseline — the CPU oracle (reference modules' arithmetic, oracle/) timed on this box's host cores
@@ -185,19 +186,15 @@ def measure_aggregation(dev, iters: int = 20):
     gout = torch.randn(n, h, generator=g).to(dev)
     w, b, eps = torch.randn(h, generator=g).to(dev), torch.randn(h, generator=g).to(dev), torch.zeros(1, device=dev)
     out = torch.empty_like(x)
-    L = _lib.lib()
-    nb = L.rc_gine_aggr_bwd_nblocks(n, h)
-    part = torch.empty(nb, 3, h, device=dev)
+    from raincast_gnn_b200 import kernels as K
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
+    sg.tiles(h)                    # the product path: station tiles (built once per graph, like the CSR)
 
     def fwd():
-        _lib.check(L.rc_gine_aggr_fwd(x.data_ptr(), sg.rowptr.data_ptr(), sg.col.data_ptr(), sg.attr.data_ptr(), w.data_ptr(),
-                                      b.data_ptr(), eps.data_ptr(), out.data_ptr(), n, h, st))
+        K.gine_aggr_fwd(x, sg, w, b, eps, out)
 
     def bwd():
-        _lib.check(L.rc_gine_aggr_bwd(gout.data_ptr(), x.data_ptr(), sg.t_rowptr.data_ptr(), sg.t_dst.data_ptr(), sg.t_attr.data_ptr(),
-                                      w.data_ptr(), b.data_ptr(), eps.data_ptr(), None, out.data_ptr(), part.data_ptr(), n, h, st))
+        K.gine_aggr_bwd(gout, x, sg, w, b, eps, None, out)
     res = {}
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
         for _ in range(3):
@@ -254,17 +251,25 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     def timed_loop(e2e: bool):
-        """K steps, each bracketed by its own CUDA events (the L2 flush between steps is outside the events)."""
+        """K steps, each bracketed by its own CUDA events (the L2 flush between steps is outside the events).
+        e2e: every timed interval contains one complete host -> device copy of a batch (the NEXT step's, started
+        right after the start event on the copy stream and waited for before the end event - the engine's input
+        prefetch, as train.py uses it), the move of the current batch into the step's inputs, the step, and the
+        device -> host read of its loss."""
         total_ms = 0.0
+        if e2e:
+            eng.prefetch(*batches[0])
         for i in range(W + K_steps):
             flush.zero_()
             a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if e2e:
-                eng.load_batch(*batches[i % len(batches)])
+                eng.take_prefetched()
+                eng.prefetch(*batches[(i + 1) % len(batches)])
             loss = eng.step()
             if e2e:
                 losses_host[i].copy_(loss[0], non_blocking=True)
+                eng.wait_prefetch()
             c.record()
             if i >= W:
                 c.synchronize()
@@ -305,7 +310,7 @@ def run_b200(args):
         if not args.no_roofline:
             res, bf, bb, n, e = measure_aggregation(dev)
             ach = bf / (res["fwd"] * 1e-3) / 1e9
-            line["roofline"] = {"bound": "hbm", "kernel": "gine_aggr_fwd_kernel<1> (config 4: 100k nodes, 2 978 560 edges, H=128)",
+            line["roofline"] = {"bound": "hbm", "kernel": "gine_aggr_fwd_tiled_kernel (config 4: 100k nodes, 2 978 560 edges, H=128; station tiles, L2 flushed before every launch)",
                                 "achieved": ach, "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} hbm_gbs (burst copy)",
                                 "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                                 "algorithmic_bytes": bf, "us_per_launch": res["fwd"] * 1e3,
@@ -314,7 +319,9 @@ def run_b200(args):
                                         "frac": bb / (res["bwd"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    line["roofline"]["traffic"] = json.load(f).get("gine_aggr_fwd_dram_bytes")
+                    tr = json.load(f)
+                line["roofline"]["traffic"] = tr.get("gine_aggr_fwd_dram_bytes")
+                line["roofline"]["bwd"]["traffic"] = tr.get("gine_aggr_bwd_dram_bytes")
             except OSError:
                 pass
         if world == 1 and not args.no_cpu_baseline:

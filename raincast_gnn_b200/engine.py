@@ -87,6 +87,12 @@ class TrainEngine:
         self.mode = mode
         self._prog = None
         self._side = torch.cuda.Stream(device=dev)      # weight-gradient work overlaps the data-gradient chain
+        # input prefetch: the next batch travels host -> staging buffers on a copy stream while the current step runs
+        self._copy = torch.cuda.Stream(device=dev)
+        self._stage = None                              # (x, ensemble, y) staging buffers, allocated on first use
+        self._staged = torch.cuda.Event()               # the staged batch has landed
+        self._stage_free = torch.cuda.Event()           # the staged batch has been moved into the step's inputs
+        self._has_staged = False
         self._graph = None
         self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
 
@@ -225,6 +231,35 @@ class TrainEngine:
         self.x.copy_(x, non_blocking=non_blocking)
         self.ens.copy_(ensemble, non_blocking=non_blocking)
         self.y.copy_(y, non_blocking=non_blocking)
+
+    def prefetch(self, x, ensemble, y):
+        """Start the host -> device copy of the NEXT batch (pinned host tensors) on the copy stream; it overlaps the
+        step that is running.  `take_prefetched` moves it into the step's inputs."""
+        if self._stage is None:
+            self._stage = tuple(torch.empty_like(t) for t in (self.x, self.ens, self.y))
+            self._stage_free.record(torch.cuda.current_stream(self.device))
+        self._copy.wait_event(self._stage_free)
+        with torch.cuda.stream(self._copy):
+            for dst, src in zip(self._stage, (x, ensemble, y)):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record(self._copy)
+        self._has_staged = True
+
+    def wait_prefetch(self):
+        """Make the current stream wait for the copy started by `prefetch` (e.g. before an end-of-step timestamp)."""
+        if self._has_staged:
+            torch.cuda.current_stream(self.device).wait_event(self._staged)
+
+    def take_prefetched(self):
+        """Move the prefetched batch into the step's static inputs (device -> device, on the current stream)."""
+        if not self._has_staged:
+            raise _lib.RcError("take_prefetched without a prefetch")
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged)
+        for dst, src in zip((self.x, self.ens, self.y), self._stage):
+            dst.copy_(src, non_blocking=True)
+        self._stage_free.record(cur)
+        self._has_staged = False
 
     def step(self):
         """One training step on the batch in the static buffers; returns the device-resident loss (float64 [1])."""

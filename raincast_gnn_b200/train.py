@@ -78,14 +78,27 @@ def run_epoch_autograd(model, loader, optimizer, device) -> float:
 
 
 def run_epoch_engine(engine: TrainEngine, loader) -> float:
-    """The same pass through the captured step: H2D of x / ensemble / y, replay, (all-reduce,) fused AdamW."""
+    """The same pass through the captured step: the next batch's H2D copy of x / ensemble / y runs on a copy stream
+    while the current step replays, then (all-reduce,) fused AdamW."""
     engine.loss_sum.zero_()
     done = 0
-    for batch in loader:
-        if batch.x.shape[0] == engine.m:        # the captured step has a fixed shape: a ragged last batch is skipped
-            engine.load_batch(batch.x, batch.ensemble, batch.y)
-            engine.step()
-            done += 1
+    pinned = torch.cuda.is_available()
+    it = (b for b in loader if b.x.shape[0] == engine.m)   # the captured step has a fixed shape: a ragged last batch is skipped
+
+    def start(batch):
+        host = [t.pin_memory() if pinned and t.device.type == "cpu" and not t.is_pinned() else t for t in (batch.x, batch.ensemble, batch.y)]
+        engine.prefetch(*host)
+        return host                                  # keeps the pinned tensors alive until the copy has run
+    batch = next(it, None)
+    held = start(batch) if batch is not None else None
+    while batch is not None:
+        engine.take_prefetched()
+        batch = next(it, None)
+        nxt = start(batch) if batch is not None else None
+        engine.step()
+        held = nxt
+        done += 1
+    del held
     return engine.loss_sum.item() / max(done, 1)
 
 

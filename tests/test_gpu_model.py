@@ -267,6 +267,42 @@ def test_engine_matches_module_path_and_reference_trajectory(dev, golden_model):
     assert torch.equal(sd2["aggr.weight"], model.aggr.weight.detach())
 
 
+def test_engine_prefetch_matches_load_batch(dev):
+    """Input prefetch (pinned host batch -> staging buffers on the copy stream, overlapping the running step) feeds the
+    step exactly what load_batch does: identical loss trajectories over alternating batches."""
+    from raincast_gnn_b200 import _lib
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    c, batch, _, sd = build_case("ref_mixed_u", dev)
+    g = torch.Generator().manual_seed(5)
+    hosts = []
+    for _ in range(3):
+        hosts.append(tuple(t.pin_memory() for t in (torch.randn(batch.x.shape, generator=g), torch.randn(batch.ensemble.shape, generator=g),
+                                                      batch.y.detach().cpu().clone())))
+    trajs = []
+    for prefetch in (False, True):
+        model = GNN(**_model_kw(c))
+        model.load_state_dict(sd)
+        model.to(dev).train()
+        eng = TrainEngine(model, batch.station_graph, batch.x.shape[0], c["em"], c["f"], lr=1e-3).capture()
+        traj = []
+        if prefetch:
+            eng.prefetch(*hosts[0])
+        for i in range(6):
+            if prefetch:
+                eng.take_prefetched()
+                eng.prefetch(*hosts[(i + 1) % 3])
+            else:
+                eng.load_batch(*hosts[i % 3])
+            traj.append(eng.step().clone())
+        torch.cuda.synchronize()
+        trajs.append([float(t) for t in traj])
+    assert trajs[0] == trajs[1]
+    eng.take_prefetched()
+    with pytest.raises(_lib.RcError):
+        eng.take_prefetched()
+
+
 def test_step_program_matches_graph_mode(dev):
     """The persistent step program (one cooperative kernel) and the CUDA-graph schedule of separate kernels are the
     same arithmetic: identical loss trajectories, parameters, Adam state and BatchNorm buffers after 4 steps."""
