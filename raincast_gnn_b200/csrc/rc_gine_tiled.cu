@@ -114,17 +114,17 @@ __device__ __forceinline__ void produce_tiles(const float* __restrict__ src, siz
     unsigned char* blk = rows + t.rows_bytes;
     const unsigned char* my_src = base + (size_t)my_id * row_stride;   // start of this lane's row
     if (it >= 2) mbar_wait(&ctrl->empty[b], ((it >> 1) & 1) ^ 1);      // every consumer warp is done with this buffer
-    // gathered rows: the row addresses are broadcast lane by lane; every lane copies 16 bytes of every row of the warp
+    // the tile's block of group / entry records: contiguous, 16 bytes per thread per pass
+    const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.blocks) + (size_t)b0 * 16;
+    for (int u = warp * 32 + lane; u < bunits; u += 32 * kProdWarps)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(blk + 16 * u)), "l"(bsrc + 16 * (size_t)u) : "memory");
+    // gathered rows: the row addresses are broadcast lane by lane; every lane moves 16 bytes of every row of the warp
     const int cnt = nst > warp ? (nst - warp + kProdWarps - 1) / kProdWarps : 0;
     unsigned char* dst0 = rows + (size_t)warp * kTileRowBytes + 16 * lane;
     for (int k = 0; k < cnt; ++k) {
       const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)my_src, k) + 16 * lane;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst0 + k * (kProdWarps * kTileRowBytes))), "l"(sp) : "memory");
     }
-    // the tile's block of group / entry records: contiguous, 16 bytes per thread per pass
-    const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.blocks) + (size_t)b0 * 16;
-    for (int u = warp * 32 + lane; u < bunits; u += 32 * kProdWarps)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(blk + 16 * u)), "l"(bsrc + 16 * (size_t)u) : "memory");
     const int next = tile + step;
     if (next < t.n_tiles) {
       s0 = __ldg(t.tile_stage_ptr + next); nst = __ldg(t.tile_stage_ptr + next + 1) - s0;
@@ -133,7 +133,9 @@ __device__ __forceinline__ void produce_tiles(const float* __restrict__ src, siz
     }
     if (warp == 0 && lane == 0) ctrl->counter[b] = 0;   // nobody claims from this buffer between its release and the arrivals below
     if (BIAS) {
-      // every lane rewrites the 16 bytes it copied itself (no other thread involved): x_j -> (x_j + b) * 2^-64
+      // every lane rewrites the 16 bytes it copied itself (no other thread involved): x_j -> (x_j + b) * 2^-64.
+      // (Staging through registers instead - LDG, FMA, STS - saves two shared-memory wavefronts per 128 bytes but
+      // was measured slower, 86 us against 70 us on config 4: the producers become latency bound.)
       asm volatile("cp.async.wait_all;" ::: "memory");
       for (int k = 0; k < cnt; ++k) {
         float4* p = reinterpret_cast<float4*>(dst0 + k * (kProdWarps * kTileRowBytes));
@@ -236,7 +238,6 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
   }
   const float self_scale = 1.0f + __ldg(eps_ptr);
   const float4 ws = make_float4(w.x * kDown, w.y * kDown, w.z * kDown, w.w * kDown);
-  const float* xc = x + 128 * c + 4 * lane;
   float* hc = h + 128 * c + 4 * lane;
   int it = 0;
   for (int tile = first; tile < t.n_tiles; tile += step, ++it) {
@@ -251,6 +252,7 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
     for (int grp = claim_item(&ctrl->counter[bf], lane); grp < n_items; grp = claim_item(&ctrl->counter[bf], lane)) {
       const unsigned char* gp = blk + 16 + 48 * grp;
       const int4 u0 = ldsi4(gp), u1 = ldsi4(gp + 16);
+      const int u2w = *reinterpret_cast<const int*>(gp + 44);
       float4 acc[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -263,15 +265,17 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
       p = fwd_class<6>(acc, p, (unsigned)u1.z >> 16, rl, ws);
       p = fwd_class<7>(acc, p, u1.w, rl, ws);
       const int node[3] = {u0.x, u0.y, u0.z};
+      const unsigned char* self = rl + u2w;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (node[k] < 0) break;                      // rows of a group are packed to the front
-        const float4 xi = ldg4(xc + (size_t)node[k] * hidden);      // the staged copy carries the bias: x_i comes from L2
+        // the staged copy of x_i carries the bias: x_i = (x_i + b) - b, one rounding of size ulp(x_i + b) / 2
+        const float4 xs = lds4(self + k * kTileRowBytes);
         float4 o;
-        o.x = fmaf(self_scale, xi.x, acc[k].x * kUp);
-        o.y = fmaf(self_scale, xi.y, acc[k].y * kUp);
-        o.z = fmaf(self_scale, xi.z, acc[k].z * kUp);
-        o.w = fmaf(self_scale, xi.w, acc[k].w * kUp);
+        o.x = fmaf(self_scale, fmaf(xs.x, kUp, -b.x), acc[k].x * kUp);
+        o.y = fmaf(self_scale, fmaf(xs.y, kUp, -b.y), acc[k].y * kUp);
+        o.z = fmaf(self_scale, fmaf(xs.z, kUp, -b.z), acc[k].z * kUp);
+        o.w = fmaf(self_scale, fmaf(xs.w, kUp, -b.w), acc[k].w * kUp);
         st4(hc + (size_t)node[k] * hidden, o);
       }
     }
