@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL prints its version banner on stdout; the contract is ONE JSON line there
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 B_PER_GPU, N_STATIONS, MEMBERS, FEATS, HIDDEN, LAYERS = 8, 122, 11, 35, 128, 4

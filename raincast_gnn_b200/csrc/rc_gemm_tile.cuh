@@ -149,8 +149,84 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
     store_tile(0);
   }
   __syncthreads();
+  // Warp-split reduction for the latency-bound shape (8-row tile, 128-long slices - every Linear of the reference
+  // step at B = 8 graphs): warp w takes reduction indices [16 w, 16 w + 16) of every slice for ALL eight rows instead
+  // of the whole reduction for one row, so that the CTA reads the 64 KB weight tile from shared memory
+  // once instead of eight times (the shared-memory pipe, not FFMA, bounded this shape); the eight partial
+  // [8 x 128] tiles meet in shared memory and warp w sums row w in a fixed order.
+  constexpr bool kWarpSplit = (RM == 1 && kRK == 128 && AL == RC_A_ROW);
+  if (kWarpSplit) {
+    float acc8[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc8[i][j] = 0.f;
+    int cur = 0;
+    for (int t = t_beg; t < t_end; ++t) {
+      const bool more = t + 1 < t_end;
+      if (more) load_tile(t + 1);
+      const float* as = As + cur * A_STAGE;
+      const float* bs = Bs + cur * B_STAGE;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r4 = warp * 4 + q;
+        float a[8][4], b[4][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = ld4(as + i * SA + r4 * 4);
+          a[i][0] = v.x; a[i][1] = v.y; a[i][2] = v.z; a[i][3] = v.w;
+        }
+        if (BL == RC_B_COL) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = ld4(bs + (lane + 32 * j) * SB + r4 * 4);
+            b[0][j] = v.x; b[1][j] = v.y; b[2][j] = v.z; b[3][j] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const float4 v = ld4(bs + (r4 * 4 + rr) * SB + 4 * lane);
+            b[rr][0] = v.x; b[rr][1] = v.y; b[rr][2] = v.z; b[rr][3] = v.w;
+          }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc8[i][j] = fmaf(a[i][rr], b[rr][j], acc8[i][j]);
+      }
+      if (more) store_tile(cur ^ 1);
+      __syncthreads();                // (last slice: every warp is done with the operand tiles, they become the partial buffer)
+      cur ^= 1;
+    }
+    float* part = smem;               // [8 warps][8 rows][kBN]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float* pr = part + (warp * 8 + i) * kBN;
+      if (BL == RC_B_COL) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[lane + 32 * j] = acc8[i][j];
+      } else {
+        st4(pr + 4 * lane, make_float4(acc8[i][0], acc8[i][1], acc8[i][2], acc8[i][3]));
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float* pr = part + (w * 8 + warp) * kBN;
+      if (BL == RC_B_COL) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[0][j] += pr[lane + 32 * j];
+      } else {
+        const float4 v = ld4(pr + 4 * lane);
+        acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+      }
+    }
+    __syncthreads();                  // the epilogue reuses the front of shared memory
+  }
   int cur = 0;
-  for (int t = t_beg; t < t_end; ++t) {
+  for (int t = kWarpSplit ? t_end : t_beg; t < t_end; ++t) {
     const bool more = t + 1 < t_end;
     if (more) load_tile(t + 1);
     const float* as = As + cur * A_STAGE;

@@ -243,6 +243,37 @@ def deepsets_bwd(P, saved, d_emb, G):
 
 
 # --------------------------------------------------------------------------------------------- dim_red
+def dimred_prepack(P, f):
+    """dim_red.weight is [H, F + H] with F = 35: neither half of a row starts on a 16-byte boundary, and the GEMM
+    falls back to scalar loads for the whole 128 x 163 operand (measured 12.4 us against 5.4 us at the reference
+    shape, forward and backward-data alike).  The engine calls this at the start of a step: two strided copies on the
+    side stream (they overlap the DeepSets kernels) split the weight into aligned halves wx [H, F padded to 4] and
+    we [H, H]; dimred_fwd / dimred_bwd pick them up.  The parameter itself keeps the reference layout."""
+    if RECORD.active or SIDE.stream is None:
+        return
+    w = P["dimred_w"]
+    n, ldw = w.shape
+    pack = P.get("_dimred_pack")
+    if pack is None:
+        fpad = (f + 3) // 4 * 4
+        pack = P["_dimred_pack"] = {"wx": torch.zeros((n, fpad), dtype=torch.float32, device=w.device),
+                                    "we": torch.empty((n, ldw - f), dtype=torch.float32, device=w.device), "f": f}
+    with on_side(w):
+        pack["wx"][:, :f].copy_(w.detach()[:, :f])
+        pack["we"].copy_(w.detach()[:, f:])
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+    pack["ready"] = ev
+
+
+def _dimred_pack(P, f):
+    """The aligned halves prepared for this step, or None (eager / step-program paths use the parameter directly)."""
+    pack = P.get("_dimred_pack")
+    if pack is None or pack.get("ready") is None or pack["f"] != f or RECORD.active:
+        return None
+    return pack
+
+
 def dimred_fwd(P, x, emb):
     """Linear(cat([x, emb])) without materialising the cat: two reduction segments (models/gnn.py:134-135)."""
     m, f = x.shape
@@ -250,8 +281,14 @@ def dimred_fwd(P, x, emb):
     w = P["dimred_w"]
     n, ldw = w.shape
     y = _new((m, n), torch.float32, x.device)
-    gemm(m, n, f, operand(x, f), operand(w, ldw), y, n, bias=P["dimred_b"],
-         a2=emb, lda2=h_in, b2=w.reshape(-1)[f:], ldb2=ldw, k2=h_in)
+    pack = _dimred_pack(P, f)
+    if pack is not None:
+        torch.cuda.current_stream().wait_event(pack["ready"])
+        gemm(m, n, f, operand(x, f), operand(pack["wx"], pack["wx"].shape[1]), y, n, bias=P["dimred_b"],
+             a2=emb, lda2=h_in, b2=pack["we"], ldb2=h_in, k2=h_in)
+    else:
+        gemm(m, n, f, operand(x, f), operand(w, ldw), y, n, bias=P["dimred_b"],
+             a2=emb, lda2=h_in, b2=w.reshape(-1)[f:], ldb2=ldw, k2=h_in)
     return y, (x, emb)
 
 
@@ -267,6 +304,10 @@ def dimred_bwd(P, saved, dy, G):
         linear_bwd_weight(operand(dy, n), operand(x, f), m, n, f, dw[:, :f], G["dimred_b"], sink, dw_ld=ldw)
         linear_bwd_weight(operand(dy, n), operand(emb, h_in), m, n, h_in, dw[:, f:], None, sink, dw_ld=ldw)
         sink.flush()
+    pack = _dimred_pack(P, f)
+    if pack is not None:
+        pack["ready"] = None                 # one step only: the optimizer changes the weight next
+        return linear_bwd_data(dy, pack["we"], w_ld=h_in, w_col0=0, k=h_in)
     return linear_bwd_data(dy, w, w_ld=ldw, w_col0=f, k=h_in)
 
 
