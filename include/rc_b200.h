@@ -120,6 +120,8 @@ typedef struct rc_gine_tiles {
   int32_t n_tiles; int32_t max_staged;       /* most rows any tile stages                      */
   int32_t max_block_bytes; int32_t row_bytes; /* largest tile block; 4 * hidden                 */
   const int32_t* tile_stage_ptr; const int32_t* tile_blk_ptr; const int32_t* stage_id; const int32_t* blocks;
+  int32_t* sched;   /* device int32[8], zero when handed over: the forward kernel's tile counters (it leaves them
+                       zero; one launch at a time per rc_gine_tiles)                                        */
 } rc_gine_tiles;
 /* max_src / max_block_bytes that fit one CTA at `hidden` columns (128 | hidden <= 512). */
 int rc_gine_tiles_limits(int hidden, int* max_src, int* max_block_bytes);

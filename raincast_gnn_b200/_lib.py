@@ -31,7 +31,7 @@ class rc_csr(C.Structure):
 
 class rc_gine_tiles(C.Structure):
     _fields_ = [("n_tiles", C.c_int32), ("max_staged", C.c_int32), ("max_block_bytes", C.c_int32), ("row_bytes", C.c_int32)] + [
-        (n, _fp) for n in ("tile_stage_ptr", "tile_blk_ptr", "stage_id", "blocks")]
+        (n, _fp) for n in ("tile_stage_ptr", "tile_blk_ptr", "stage_id", "blocks", "sched")]
 
 
 class rc_operand(C.Structure):

@@ -17,8 +17,10 @@
 //     rows are walked chunk by chunk (a CTA stays on one chunk, so tiles do not depend on the width)
 //   - a group's entries are sorted by class (= which of its rows use the source); one straight-line loop per class,
 //     one broadcast 16-byte record {staged offset, attr per row} per entry: no per-edge test, no global load
-//   - per (edge, 4 columns): 2 packed FMA (a*w + x_j), 4 max, 2 packed adds.  The bias is taken out of the loop:
-//     relu(x_j + a*w + b) = max(x_j + a*w, -b) + b, so a row adds degree * b once at the end
+//   - the ReLU rides on the FMA: with operands scaled by 2^-64 (exact), fma.rn.sat clamps a*w + x_j + b to [0, 1],
+//     i.e. computes relu for every message below 2^64.  Per (edge, 4 columns): 4 FFMA.SAT + 2 packed adds = 9 issue
+//     cycles per sub-partition; FFMA2 + 4 FMNMX + 2 FADD2 measured 14.6 (tools/ubench/pipes.cu: FMNMX issues every
+//     second cycle and does not overlap the FMA pipe on B200)
 //   - deterministic: the summation order is fixed by the tiles (class by class, not the CSR slot order of the
 //     untiled kernels - results agree to rounding, not bit for bit)
 // Backward: the transpose tiles stage g rows; the ReLU mask is recomputed from the row's own x and the edge attr
@@ -43,7 +45,7 @@ constexpr int kProdWarps = RC_PROD_WARPS;  // producer warps: warp w runs on sub
 static_assert(32 * kProdWarps * 512 >= 227 * 1024 / 2, "one staged row per producer lane");
 constexpr int kFwdThreads = RC_FWD_THREADS;
 constexpr int kBwdThreads = RC_BWD_THREADS;
-constexpr int kCtrlBytes = 64;            // full[2], empty[2] mbarriers + two item counters
+constexpr int kCtrlBytes = 64;            // full[2], empty[2] mbarriers, two item counters, two claimed tile indices
 
 // scale factors of the saturating-FMA ReLU (see relu_acc / masked_acc)
 constexpr float kDown = 5.421010862427522e-20f;   // 2^-64
@@ -57,11 +59,13 @@ struct TilesP {
   const int* __restrict__ tile_blk_ptr;
   const int* __restrict__ stage_id;
   const int* __restrict__ blocks;
+  int* sched;        // [8] zero between launches: next tile per column chunk [0..3], CTAs out of tiles per chunk [4..7]
 };
 
 struct Ctrl {
   unsigned long long full[2], empty[2];
   int counter[2];
+  int claimed[2];    // dynamic schedule: the tile index the producers claimed for a buffer (>= n_tiles: no tile left)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,68 +98,74 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
 // w + l * kProdWarps of every tile (32 * kProdWarps >= the most rows a buffer can hold): the tile's ranges and the
 // lane's row id are fetched BEFORE waiting for the buffer, so that a released buffer is refilled without a trip to
 // global memory first.
-template <bool BIAS>
+// DYN: tiles are claimed from a global counter (tile order = build order; every CTA keeps claiming until the counter
+// runs past the last tile, the last CTA to get there zeroes the counters for the next launch) instead of the static
+// round robin `first + k * step`.  Which CTA runs which tile then varies from launch to launch; the forward results do
+// not depend on it, the backward keeps the static schedule so that its per-CTA partial sums stay reproducible.
+template <bool DYN>
 __device__ __forceinline__ void produce_tiles(const float* __restrict__ src, size_t row_stride, const TilesP& t, int first, int step,
-                                              unsigned char* smem, Ctrl* ctrl, int lane, int warp,
-                                              float4 bias = make_float4(0.f, 0.f, 0.f, 0.f)) {
+                                              unsigned char* smem, Ctrl* ctrl, int lane, int warp, int chunk = 0) {
   const unsigned char* base = reinterpret_cast<const unsigned char*>(src);
   const int mine = warp + lane * kProdWarps;
-  int it = 0;
-  // ranges and row id of the first tile; those of tile i + 1 are fetched while the copies of tile i are in flight
+  auto claim = [&](int it, int prev) -> int {
+    if (!DYN) return it == 0 ? first : prev + step;
+    if (warp == 0 && lane == 0) ctrl->claimed[it & 1] = atomicAdd(t.sched + chunk, 1);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kProdWarps) : "memory");      // producer warps only
+    return ctrl->claimed[it & 1];
+  };
+  // ranges and row id of a tile are fetched while the copies of the tile before it are in flight
   int s0 = 0, nst = 0, b0 = 0, bunits = 0, my_id = 0;
-  if (first < t.n_tiles) {
-    s0 = __ldg(t.tile_stage_ptr + first); nst = __ldg(t.tile_stage_ptr + first + 1) - s0;
-    b0 = __ldg(t.tile_blk_ptr + first); bunits = __ldg(t.tile_blk_ptr + first + 1) - b0;
-    my_id = mine < nst ? __ldg(t.stage_id + s0 + mine) : 0;
-  }
-  for (int tile = first; tile < t.n_tiles; tile += step, ++it) {
+  auto fetch = [&](int tile) {
+    if (tile < t.n_tiles) {
+      s0 = __ldg(t.tile_stage_ptr + tile); nst = __ldg(t.tile_stage_ptr + tile + 1) - s0;
+      b0 = __ldg(t.tile_blk_ptr + tile); bunits = __ldg(t.tile_blk_ptr + tile + 1) - b0;
+      my_id = mine < nst ? __ldg(t.stage_id + s0 + mine) : 0;
+    }
+  };
+  int tile = claim(0, 0);
+  fetch(tile);
+  for (int it = 0;; ++it) {
     const int b = it & 1;
+    if (!DYN && tile >= t.n_tiles) break;
     unsigned char* rows = smem + (size_t)b * t.buf_bytes;
     unsigned char* blk = rows + t.rows_bytes;
     const unsigned char* my_src = base + (size_t)my_id * row_stride;   // start of this lane's row
     if (it >= 2) mbar_wait(&ctrl->empty[b], ((it >> 1) & 1) ^ 1);      // every consumer warp is done with this buffer
-    // the tile's block of group / entry records: contiguous, 16 bytes per thread per pass
-    const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.blocks) + (size_t)b0 * 16;
-    for (int u = warp * 32 + lane; u < bunits; u += 32 * kProdWarps)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(blk + 16 * u)), "l"(bsrc + 16 * (size_t)u) : "memory");
-    // gathered rows: the row addresses are broadcast lane by lane; every lane moves 16 bytes of every row of the warp
-    const int cnt = nst > warp ? (nst - warp + kProdWarps - 1) / kProdWarps : 0;
-    unsigned char* dst0 = rows + (size_t)warp * kTileRowBytes + 16 * lane;
-    for (int k = 0; k < cnt; ++k) {
-      const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)my_src, k) + 16 * lane;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst0 + k * (kProdWarps * kTileRowBytes))), "l"(sp) : "memory");
-    }
-    const int next = tile + step;
-    if (next < t.n_tiles) {
-      s0 = __ldg(t.tile_stage_ptr + next); nst = __ldg(t.tile_stage_ptr + next + 1) - s0;
-      b0 = __ldg(t.tile_blk_ptr + next); bunits = __ldg(t.tile_blk_ptr + next + 1) - b0;
-      my_id = mine < nst ? __ldg(t.stage_id + s0 + mine) : 0;
-    }
-    if (warp == 0 && lane == 0) ctrl->counter[b] = 0;   // nobody claims from this buffer between its release and the arrivals below
-    if (BIAS) {
-      // every lane rewrites the 16 bytes it copied itself (no other thread involved): x_j -> (x_j + b) * 2^-64.
-      // (Staging through registers instead - LDG, FMA, STS - saves two shared-memory wavefronts per 128 bytes but
-      // was measured slower, 86 us against 70 us on config 4: the producers become latency bound.)
-      asm volatile("cp.async.wait_all;" ::: "memory");
+    if (tile < t.n_tiles) {
+      // the tile's block of group / entry records: contiguous, 16 bytes per thread per pass
+      const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(t.blocks) + (size_t)b0 * 16;
+      for (int u = warp * 32 + lane; u < bunits; u += 32 * kProdWarps)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(blk + 16 * u)), "l"(bsrc + 16 * (size_t)u) : "memory");
+      // gathered rows: the row addresses are broadcast lane by lane; every lane moves 16 bytes of every row of the warp
+      const int cnt = nst > warp ? (nst - warp + kProdWarps - 1) / kProdWarps : 0;
+      unsigned char* dst0 = rows + (size_t)warp * kTileRowBytes + 16 * lane;
       for (int k = 0; k < cnt; ++k) {
-        float4* p = reinterpret_cast<float4*>(dst0 + k * (kProdWarps * kTileRowBytes));
-        float4 v = *p;
-        v.x = fmaf(v.x, kDown, bias.x); v.y = fmaf(v.y, kDown, bias.y);
-        v.z = fmaf(v.z, kDown, bias.z); v.w = fmaf(v.w, kDown, bias.w);
-        *p = v;
+        const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)my_src, k) + 16 * lane;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst0 + k * (kProdWarps * kTileRowBytes))), "l"(sp) : "memory");
       }
-      mbar_arrive(&ctrl->full[b]);          // release: the rows, the records and the counter are visible to whoever sees the phase
-    } else {
-      if (warp == 0 && lane == 0) mbar_arrive(&ctrl->full[b]);    // release: orders the counter store before the consumers' claims
-      mbar_arrive_on_copies(&ctrl->full[b]);
     }
+    const bool last = tile >= t.n_tiles;      // (dynamic schedule only: tells the consumers to stop)
+    if (warp == 0 && lane == 0) {
+      ctrl->counter[b] = last ? (1 << 30) : 0;   // nobody claims from this buffer between its release and the arrivals below
+      mbar_arrive(&ctrl->full[b]);               // release: orders the counter store before the consumers' claims
+    }
+    mbar_arrive_on_copies(&ctrl->full[b]);
+    if (last) {
+      if (warp == 0 && lane == 0 && atomicAdd(t.sched + 4 + chunk, 1) == step - 1) {
+        t.sched[chunk] = 0;                      // every CTA of this chunk has made its last claim
+        t.sched[4 + chunk] = 0;
+      }
+      break;
+    }
+    tile = claim(it + 1, tile);
+    fetch(tile);
   }
 }
 
-__device__ __forceinline__ void init_ctrl(Ctrl* ctrl, int consumer_warps, int producer_arrivals) {
+__device__ __forceinline__ void init_ctrl(Ctrl* ctrl, int consumer_warps) {
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&ctrl->full[b], producer_arrivals);
+      mbar_init(&ctrl->full[b], 32 * kProdWarps + 1);     // every producer lane's copies + the counter reset
       mbar_init(&ctrl->empty[b], consumer_warps);
       ctrl->counter[b] = 0;
     }
@@ -185,12 +195,20 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
   return d;
 }
 
-// acc += sat(a * ws + vs)   (ws = w kDown, vs = (x_j + b) kDown: staged that way by the producer warps)
+// acc += sat(a * ws + vs)   (ws = w kDown, vs = (x_j + b) kDown)
 __device__ __forceinline__ void relu_acc(float4& acc, float4 vs, float a, float4 ws) {
   const float2 z0 = make_float2(fma_sat(a, ws.x, vs.x), fma_sat(a, ws.y, vs.y));
   const float2 z1 = make_float2(fma_sat(a, ws.z, vs.z), fma_sat(a, ws.w, vs.w));
   const float2 s0 = __fadd2_rn(make_float2(acc.x, acc.y), z0), s1 = __fadd2_rn(make_float2(acc.z, acc.w), z1);
   acc = make_float4(s0.x, s0.y, s1.x, s1.y);
+}
+
+// The staged rows are raw x_j; every entry folds bias and scale in with four FMAs, shared by the rows of the group:
+// vs = x_j * 2^-64 + b * 2^-64.  (Letting the producer warps rewrite the staged rows once per tile instead measured
+// the same on config 4 and 3 % slower on batched reference graphs: two more shared-memory wavefronts per 128 bytes
+// and a producer that has to wait for its own copies.)
+__device__ __forceinline__ float4 prebias(float4 v, float4 bs) {
+  return make_float4(fmaf(v.x, kDown, bs.x), fmaf(v.y, kDown, bs.y), fmaf(v.z, kDown, bs.z), fmaf(v.w, kDown, bs.w));
 }
 
 template <int MASK>
@@ -203,17 +221,21 @@ __device__ __forceinline__ void fwd_apply(float4 (&acc)[3], float4 v, int4 rec, 
 // the n entries of one class, two in flight; returns the next class's first entry
 template <int MASK>
 __device__ __forceinline__ const unsigned char* fwd_class(float4 (&acc)[3], const unsigned char* p, int n, const unsigned char* rl,
-                                                          float4 w) {
+                                                          float4 w, float4 bs) {
 #pragma unroll 1
   for (; n >= 2; n -= 2, p += 32) {
     const int4 r0 = ldsi4(p), r1 = ldsi4(p + 16);
-    const float4 v0 = lds4(rl + r0.x), v1 = lds4(rl + r1.x);
+    float4 v0 = lds4(rl + r0.x), v1 = lds4(rl + r1.x);
+    v0 = prebias(v0, bs);
+    v1 = prebias(v1, bs);
     fwd_apply<MASK>(acc, v0, r0, w);
     fwd_apply<MASK>(acc, v1, r1, w);
   }
   if (n) {
     const int4 r0 = ldsi4(p);
-    fwd_apply<MASK>(acc, lds4(rl + r0.x), r0, w);
+    float4 v0 = lds4(rl + r0.x);
+    v0 = prebias(v0, bs);
+    fwd_apply<MASK>(acc, v0, r0, w);
     p += 16;
   }
   return p;
@@ -228,24 +250,23 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 2 * (size_t)t.buf_bytes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x % chunks, first = blockIdx.x / chunks, step = gridDim.x / chunks;
-  init_ctrl(ctrl, kFwdThreads / 32 - kProdWarps, 32 * kProdWarps);
+  init_ctrl(ctrl, kFwdThreads / 32 - kProdWarps);
   const float4 w = ldg4(w_edge + 4 * lane + 128 * c), b = ldg4(b_edge + 4 * lane + 128 * c);
+  const float4 bs = make_float4(b.x * kDown, b.y * kDown, b.z * kDown, b.w * kDown);
   if (warp < kProdWarps) {
-    // the staged rows become (x_j + b_edge) * 2^-64
-    produce_tiles<true>(x + 128 * c, (size_t)hidden * 4, t, first, step, smem, ctrl, lane, warp,
-                        make_float4(b.x * kDown, b.y * kDown, b.z * kDown, b.w * kDown));
+    produce_tiles<true>(x + 128 * c, (size_t)hidden * 4, t, first, step, smem, ctrl, lane, warp, c);
     return;
   }
   const float self_scale = 1.0f + __ldg(eps_ptr);
   const float4 ws = make_float4(w.x * kDown, w.y * kDown, w.z * kDown, w.w * kDown);
   float* hc = h + 128 * c + 4 * lane;
-  int it = 0;
-  for (int tile = first; tile < t.n_tiles; tile += step, ++it) {
+  for (int it = 0;; ++it) {
     const int bf = it & 1;
     const unsigned char* rows = smem + (size_t)bf * t.buf_bytes;
     const unsigned char* blk = rows + t.rows_bytes;
     const unsigned char* rl = rows + 16 * lane;        // this lane's 4 columns inside a staged row
     mbar_wait(&ctrl->full[bf], (it >> 1) & 1);
+    if (*reinterpret_cast<volatile int*>(&ctrl->counter[bf]) >= (1 << 30)) break;     // the producers found no tile left
     const int n_items = reinterpret_cast<const int*>(blk)[2];
     // groups are claimed in order (most edges first) from a shared counter: warps leave a tile within one short group
     // of each other whatever the degree distribution
@@ -257,25 +278,24 @@ gine_aggr_fwd_tiled_kernel(const float* __restrict__ x, const TilesP t, const fl
 #pragma unroll
       for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       const unsigned char* p = blk + u0.w;
-      p = fwd_class<1>(acc, p, u1.x & 0xffff, rl, ws);
-      p = fwd_class<2>(acc, p, (unsigned)u1.x >> 16, rl, ws);
-      p = fwd_class<3>(acc, p, u1.y & 0xffff, rl, ws);
-      p = fwd_class<4>(acc, p, (unsigned)u1.y >> 16, rl, ws);
-      p = fwd_class<5>(acc, p, u1.z & 0xffff, rl, ws);
-      p = fwd_class<6>(acc, p, (unsigned)u1.z >> 16, rl, ws);
-      p = fwd_class<7>(acc, p, u1.w, rl, ws);
+      p = fwd_class<1>(acc, p, u1.x & 0xffff, rl, ws, bs);
+      p = fwd_class<2>(acc, p, (unsigned)u1.x >> 16, rl, ws, bs);
+      p = fwd_class<3>(acc, p, u1.y & 0xffff, rl, ws, bs);
+      p = fwd_class<4>(acc, p, (unsigned)u1.y >> 16, rl, ws, bs);
+      p = fwd_class<5>(acc, p, u1.z & 0xffff, rl, ws, bs);
+      p = fwd_class<6>(acc, p, (unsigned)u1.z >> 16, rl, ws, bs);
+      p = fwd_class<7>(acc, p, u1.w, rl, ws, bs);
       const int node[3] = {u0.x, u0.y, u0.z};
       const unsigned char* self = rl + u2w;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (node[k] < 0) break;                      // rows of a group are packed to the front
-        // the staged copy of x_i carries the bias: x_i = (x_i + b) - b, one rounding of size ulp(x_i + b) / 2
-        const float4 xs = lds4(self + k * kTileRowBytes);
+        const float4 xs = lds4(self + k * kTileRowBytes);       // x_i is staged too (own rows lead the tile)
         float4 o;
-        o.x = fmaf(self_scale, fmaf(xs.x, kUp, -b.x), acc[k].x * kUp);
-        o.y = fmaf(self_scale, fmaf(xs.y, kUp, -b.y), acc[k].y * kUp);
-        o.z = fmaf(self_scale, fmaf(xs.z, kUp, -b.z), acc[k].z * kUp);
-        o.w = fmaf(self_scale, fmaf(xs.w, kUp, -b.w), acc[k].w * kUp);
+        o.x = fmaf(self_scale, xs.x, acc[k].x * kUp);
+        o.y = fmaf(self_scale, xs.y, acc[k].y * kUp);
+        o.z = fmaf(self_scale, xs.z, acc[k].z * kUp);
+        o.w = fmaf(self_scale, xs.w, acc[k].w * kUp);
         st4(hc + (size_t)node[k] * hidden, o);
       }
     }
@@ -333,7 +353,7 @@ gine_aggr_bwd_tiled_kernel(const float* __restrict__ g, const float* __restrict_
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem + 2 * (size_t)t.buf_bytes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x % chunks, first = blockIdx.x / chunks, step = gridDim.x / chunks;
-  init_ctrl(ctrl, NW - kProdWarps, 32 * kProdWarps + 1);
+  init_ctrl(ctrl, NW - kProdWarps);
   float4 dw = make_float4(0.f, 0.f, 0.f, 0.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
   double deps = 0.0;   // <g, x> cancels heavily over M*H products: float64 across rows
   if (warp < kProdWarps) {
@@ -436,7 +456,7 @@ static int buffer_budget() { return ((kSmemPerCTA - kCtrlBytes) / 2) / 16 * 16; 
 static size_t tiled_smem(const TilesP& t) { return 2 * (size_t)t.buf_bytes + kCtrlBytes; }
 
 static int check_tiles(const rc_gine_tiles* t, int hidden, const char* who) {
-  if (!t || t->n_tiles < 0 || !t->tile_stage_ptr || !t->tile_blk_ptr || !t->stage_id || !t->blocks)
+  if (!t || t->n_tiles < 0 || !t->tile_stage_ptr || !t->tile_blk_ptr || !t->stage_id || !t->blocks || !t->sched)
     return fail(RC_ERR_ARG, "%s: null tile array", who);
   if (hidden < 128 || hidden % 128 || hidden > 512) return fail(RC_ERR_ARG, "%s: hidden=%d unsupported (128 | H, H <= 512)", who, hidden);
   if (t->row_bytes != kTileRowBytes) return fail(RC_ERR_ARG, "%s: tiles must be built with row_bytes = %d (one 128-column chunk), not %d", who, kTileRowBytes, t->row_bytes);
@@ -450,7 +470,8 @@ static int check_tiles(const rc_gine_tiles* t, int hidden, const char* who) {
 
 static TilesP tiles_param(const rc_gine_tiles* t) {
   const int rows_bytes = t->max_staged * kTileRowBytes;
-  return TilesP{t->n_tiles, rows_bytes, rows_bytes + t->max_block_bytes, t->tile_stage_ptr, t->tile_blk_ptr, t->stage_id, t->blocks};
+  return TilesP{t->n_tiles, rows_bytes, rows_bytes + t->max_block_bytes, t->tile_stage_ptr, t->tile_blk_ptr, t->stage_id, t->blocks,
+                t->sched};
 }
 
 }  // namespace rc

@@ -80,8 +80,10 @@ class StationTiles:
         self.num_rows = num_rows
         self.n_entries = n_entries          # shared-memory row reads per pass (edges / n_entries = reuse factor)
         self.arrays = arrays
+        # tile counters of the forward kernel's dynamic schedule (zero between launches)
+        self.sched = torch.zeros(8, dtype=torch.int32, device=arrays["blocks"].device)
         self.struct = _lib.rc_gine_tiles(n_tiles, max_staged, max_block_bytes, row_bytes,
-                                         *[arrays[a].data_ptr() for a in self._ARRAYS])
+                                         *[arrays[a].data_ptr() for a in self._ARRAYS], self.sched.data_ptr())
 
     @property
     def n_staged(self) -> int:
