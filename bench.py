@@ -32,6 +32,8 @@ if ROOT not in sys.path:
 
 # NCCL prints its version banner on stdout; the contract is ONE JSON line there
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import torch  # noqa: E402
 
@@ -288,6 +290,7 @@ def run_b200(args):
         wall_dev = time.perf_counter() - t_wall
         ms_e2e = timed_loop(e2e=True)
         barrier()
+    eng.check_peers()
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -300,7 +303,8 @@ def run_b200(args):
     line = {"metric": "station-graphs/sec train (fwd+bwd+CRPS+AdamW)", "value": value, "unit": "graphs/s", "n_gpus": world,
             "steps": K_steps, "warmup": W, "ms_per_step": ms_dev / K_steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": f"dp{world} (dates sharded, one NCCL all-reduce of {eng.n_params} fp32 gradients per step)",
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": f"dp{world} (dates sharded; per step one exchange of {eng.n_params} fp32 gradients: " +
+                                      ("summed from NVLink peer memory inside the AdamW kernel)" if eng.p2p is not None else "one NCCL all-reduce)"),
                        "timing": "per-step CUDA events on the launch stream; 256 MiB L2 flush between timed steps, outside the events; max over ranks",
                        "cuda_graph": True, "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,

@@ -290,6 +290,21 @@ int rc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, void* stream);
 
+/* Data-parallel step over NVLink peer memory (the reference, train.py:55-74,185, is single device):
+ * every rank keeps its flat gradient where the other ranks of the box can read it, and
+ *     rc_p2p_barrier(slot 0)  ->  rc_p2p_adamw_step  ->  rc_p2p_barrier(slot 1)
+ * replaces ncclAllReduce + rc_adamw_step.  rc_p2p_adamw_step sums the peers' gradients in rank order (bit-identical
+ * on every rank), scales by 1/world and applies the same AdamW update as rc_adamw_step (device-side step counter).
+ *   flags       device array [world] of pointers: rank r's flag block (int32 [2][16], zero before first use) as
+ *               mapped in this process;  epochs: this rank's int32[2] (zero before first use);  timed_out:
+ *               int32[1], set if a peer did not arrive within ~10 s (the kernel then gives up instead of hanging)
+ *   peer_grads  device array [world] of pointers to the ranks' flat gradients (n floats, n % 4 == 0, 16-byte aligned)
+ * No allocation, no host synchronisation: all three calls are CUDA-graph capturable.  world <= 16. */
+int rc_p2p_barrier(int32_t* const* flags, int32_t* epochs, int rank, int world, int slot, int32_t* timed_out, void* stream);
+int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, float* exp_avg, float* exp_avg_sq,
+                      int64_t* step, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Step program: record a sequence of the calls above and run it as ONE persistent cooperative kernel
  * (replaces the ~75 launches of a train.py iteration, train.py:61-71, at shapes where launch latency dominates)

@@ -96,6 +96,8 @@ def _declare(lib):
         "rc_crps_workspace": (sz, [i]),
         "rc_crps_fwd_bwd": (i, [p, p, p, p, p, i, i, i, f, f, f, p, sz, p]),
         "rc_adamw_step": (i, [p, p, p, p, p, ll, f, f, f, f, f, f, p]),
+        "rc_p2p_barrier": (i, [p, p, i, i, i, p, p]),
+        "rc_p2p_adamw_step": (i, [p, p, i, p, p, p, ll, f, f, f, f, f, p]),
         "rc_prog_begin": (i, []),
         "rc_prog_lane": (i, [i]),
         "rc_prog_join": (i, []),

@@ -1,0 +1,134 @@
+// Data-parallel gradient exchange over NVLink peer memory (one sum of the flat fp32 gradient per step,
+// 0.84 MB at the reference shape - latency, not bandwidth).  The reference has no distributed code (train.py:55-74 is
+// single device); semantics are DDP's: the mean of the rank gradients feeds AdamW (train.py:185).
+//
+// Every rank keeps its flat gradient in a buffer the other ranks of the box can read (CUDA peer mappings; the host
+// side gets them from torch's symmetric-memory rendezvous).  One step is
+//     rc_p2p_barrier          all ranks have finished writing their gradient
+//     rc_p2p_adamw_step       g = sum_r grad_r[i] read straight from the peers (fixed rank order: every rank computes
+//                             bit-identical sums, so the replicas stay identical), scaled by 1/world, AdamW update
+//     rc_p2p_barrier          all ranks have finished reading: the gradient buffers may be overwritten
+// instead of ncclAllReduce + AdamW: no reduced gradient is ever written, and the two barriers are one store + one
+// polled load per peer.  Barriers are epoch based (a counter in local memory, never reset), so they are CUDA-graph
+// capturable and need no host-side state.
+#include "rc_misc_tile.cuh"
+
+namespace rc {
+
+constexpr int kMaxPeers = 16;
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// flags[r]: rank r's flag block (int32 [2 slots][kMaxPeers]) as mapped in this process; epochs: local int32[2].
+// Thread q tells rank q that this rank has arrived (writes the epoch into slot entry [rank] of q's block) and waits
+// for rank q's arrival in its own block.  >= : a peer may already be one barrier ahead on the same slot.
+__global__ void __launch_bounds__(32) p2p_barrier_kernel(int* const* __restrict__ flags, int* __restrict__ epochs, int rank, int world,
+                                                         int slot, int* __restrict__ timed_out) {
+  __shared__ int ep;
+  if (threadIdx.x == 0) ep = ++epochs[slot];
+  __syncthreads();
+  const int q = threadIdx.x;
+  if (q < world) {
+    __threadfence_system();                       // this device's earlier kernels' writes, system wide
+    st_release_sys(flags[q] + slot * kMaxPeers + rank, ep);
+    const int* mine = flags[rank] + slot * kMaxPeers + q;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < ep) {
+      if (clock64() - t0 > 20000000000ll) {       // ~10 s: a peer died; do not hang the device
+        atomicExch(timed_out, 1);
+        break;
+      }
+      __nanosleep(40);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) p2p_tick_kernel(const AdamTickP p) { adamw_tick_tile(p, blockIdx, gridDim); }
+
+struct P2pAdamP {
+  const float* const* grads;    // [world] peer mappings of the flat gradients
+  int world;
+  AdamP a;                      // a.grad unused
+};
+
+__global__ void __launch_bounds__(256) p2p_adamw_kernel(const P2pAdamP p) {
+  const AdamP& a = p.a;
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double t = (double)a.step[0];
+    const double bc1 = 1.0 - pow((double)a.beta1, t), bc2 = 1.0 - pow((double)a.beta2, t);
+    s_step_size = (float)((double)a.lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float decay = 1.0f - a.lr * a.weight_decay, one_m_b1 = 1.0f - a.beta1, one_m_b2 = 1.0f - a.beta2;
+  // four elements per thread (the flat buffers are padded to multiples of four floats and 16-byte aligned)
+  const long long n4 = a.n / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.world; ++r) {            // fixed order: identical sums on every rank
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.grads[r]) + i);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    float4 w = reinterpret_cast<float4*>(a.param)[i], m1 = reinterpret_cast<float4*>(a.exp_avg)[i],
+           v2 = reinterpret_cast<float4*>(a.exp_avg_sq)[i];
+    float* gp = &g.x; float* wp = &w.x; float* mp = &m1.x; float* vp = &v2.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gp[j] * a.grad_scale;
+      float pj = wp[j] * decay;
+      mp[j] = mp[j] + (gj - mp[j]) * one_m_b1;                 // lerp_
+      vp[j] = vp[j] * a.beta2 + one_m_b2 * gj * gj;            // mul_ + addcmul_
+      const float denom = sqrtf(vp[j]) / bc2_sqrt + a.eps;
+      wp[j] = pj - step_size * (mp[j] / denom);
+    }
+    reinterpret_cast<float4*>(a.param)[i] = w;
+    reinterpret_cast<float4*>(a.exp_avg)[i] = m1;
+    reinterpret_cast<float4*>(a.exp_avg_sq)[i] = v2;
+  }
+}
+
+}  // namespace rc
+
+using namespace rc;
+
+extern "C" int rc_p2p_barrier(int32_t* const* flags, int32_t* epochs, int rank, int world, int slot, int32_t* timed_out,
+                              void* stream) {
+  if (!flags || !epochs || !timed_out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || slot < 0 || slot > 1)
+    return fail(RC_ERR_ARG, "rc_p2p_barrier: bad argument (world <= %d, slot 0 or 1)", kMaxPeers);
+  p2p_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<int* const*>(flags), epochs, rank, world, slot,
+                                                                     timed_out);
+  return check_launch("p2p_barrier_kernel");
+}
+
+extern "C" int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, float* exp_avg, float* exp_avg_sq,
+                                 int64_t* step, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 void* stream) {
+  if (!param || !peer_grads || !exp_avg || !exp_avg_sq || !step || n < 0 || world < 1 || world > kMaxPeers)
+    return fail(RC_ERR_ARG, "rc_p2p_adamw_step: bad argument");
+  if (n % 4 || !aligned16(param) || !aligned16(exp_avg) || !aligned16(exp_avg_sq))
+    return fail(RC_ERR_ARG, "rc_p2p_adamw_step: n must be a multiple of 4 and the buffers 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const AdamTickP pt{reinterpret_cast<long long*>(step)};
+  p2p_tick_kernel<<<1, 32, 0, s>>>(pt);
+  if (int e = check_launch("p2p_tick_kernel")) return e;
+  if (n == 0) return RC_OK;
+  long long blocks = ceil_div_ll(n / 4, 256);
+  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  P2pAdamP p;
+  p.grads = peer_grads;
+  p.world = world;
+  p.a = AdamP{param, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<long long*>(step), n, lr, beta1, beta2, eps, weight_decay,
+              1.0f / (float)world};
+  p2p_adamw_kernel<<<(int)blocks, 256, 0, s>>>(p);
+  return check_launch("p2p_adamw_kernel");
+}

@@ -1,18 +1,22 @@
 """Graphed training step: the explicit kernel schedule of one train.py iteration (train.py:61-71)
 
     H2D batch -> DeepSets -> dim_red -> L x GINE layer -> head -> links+CRPS (value and gradient)
-              -> backward of every block -> [NCCL all-reduce of the flat gradient] -> fused AdamW
+              -> backward of every block -> [sum of the ranks' flat gradients] -> fused AdamW
 
 captured once in a CUDA graph and replayed, with parameters, gradients and Adam moments in flat buffers.
 No autograd, no per-step Python dispatch, no host sync: the loss stays on the device (train.py's per-step
 `loss.item()` becomes one read per epoch).  Data-parallel semantics are DDP's: per-rank BatchNorm
-statistics, per-rank mean over valid nodes, mean of rank gradients; the 0.84 MB gradient
-bucket is all-reduced once per step over NVLink and the 1/world factor is folded into the AdamW kernel.
+statistics, per-rank mean over valid nodes, mean of rank gradients.  The 0.84 MB gradient bucket
+is exchanged once per step over NVLink: every rank's flat gradient sits in peer-mapped memory and the AdamW kernel
+sums the ranks' gradients itself (rc_p2p_*: barrier, sum + AdamW, barrier); without peer memory (or with
+RC_DP_EXCHANGE=nccl) one NCCL all-reduce feeds rc_adamw_step, the 1/world factor folded into the kernel.
 
 The module keeps owning the parameters: `model.parameters()` become views of the flat buffer, so
 state_dict() / .ckpt saving keep working while the engine trains.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -65,7 +69,14 @@ class TrainEngine:
             for p, v in zip(params, views):
                 v.copy_(p.detach().float())
                 p.data = v
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # the flat gradient: under data parallelism it lives where the other ranks of the box can read it (NVLink peer
+        # memory), and the step sums the peers' gradients inside the AdamW kernel instead of an NCCL all-reduce
+        self.p2p = None
+        self.flat_g = None
+        if self.world > 1 and os.environ.get("RC_DP_EXCHANGE", "p2p") == "p2p":
+            self.flat_g = self._setup_peer_exchange(total, dev)
+        if self.flat_g is None:
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grads = dict(zip(self.names, _flatten_into(params, self.flat_g)))
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
@@ -95,6 +106,33 @@ class TrainEngine:
         self._has_staged = False
         self._graph = None
         self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
+
+    # ------------------------------------------------------------------ data-parallel gradient exchange
+    def _setup_peer_exchange(self, total: int, dev):
+        """Symmetric (peer-mapped) gradient buffer + barrier flags through torch's symmetric-memory rendezvous (CUDA
+        peer mappings inside one box).  Returns the gradient buffer, or None when peer memory is not available
+        (the step then uses one NCCL all-reduce, RC_DP_EXCHANGE=nccl forces that)."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else torch.distributed.group.WORLD
+            rank = torch.distributed.get_rank(group)
+            flat = symm.empty(total, dtype=torch.float32, device=dev)
+            flags = symm.empty(2 * 16, dtype=torch.int32, device=dev)
+            flat.zero_()
+            flags.zero_()
+            h_flat = symm.rendezvous(flat, group)
+            h_flags = symm.rendezvous(flags, group)
+            torch.cuda.synchronize(dev)
+            torch.distributed.barrier(group)          # every rank's flags are zero before anyone signals
+            self.p2p = {"rank": rank, "grads": h_flat.buffer_ptrs_dev, "flags": h_flags.buffer_ptrs_dev,
+                        "epochs": torch.zeros(2, dtype=torch.int32, device=dev),
+                        "timed_out": torch.zeros(1, dtype=torch.int32, device=dev), "keep": (flat, flags, h_flat, h_flags)}
+            return flat
+        except Exception as exc:                      # no symmetric memory on this box / torch build: NCCL path
+            import logging
+            logging.getLogger(__name__).warning("peer-memory gradient exchange unavailable (%s): using NCCL all-reduce", exc)
+            self.p2p = None
+            return None
 
     # ------------------------------------------------------------------ parameter dictionaries for kernels.py
     def _bind(self, model):
@@ -155,6 +193,17 @@ class TrainEngine:
         K.deepsets_bwd(Pd, s_ds, d_emb, Gd)
 
     def _optimizer(self):
+        if self.p2p is not None:
+            # barrier (gradients written) -> sum of the peers' gradients + AdamW in one kernel -> barrier (gradients read)
+            L, P, st = _lib.lib(), self.p2p, torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(L.rc_p2p_barrier(P["flags"], P["epochs"].data_ptr(), P["rank"], self.world, 0, P["timed_out"].data_ptr(), st),
+                       "rc_p2p_barrier")
+            _lib.check(L.rc_p2p_adamw_step(self.flat_p.data_ptr(), P["grads"], self.world, self.exp_avg.data_ptr(),
+                                           self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.n_params, self.lr,
+                                           self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rc_p2p_adamw_step")
+            _lib.check(L.rc_p2p_barrier(P["flags"], P["epochs"].data_ptr(), P["rank"], self.world, 1, P["timed_out"].data_ptr(), st),
+                       "rc_p2p_barrier")
+            return
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
         self._adamw_call()
@@ -233,6 +282,11 @@ class TrainEngine:
         self.ens.copy_(ensemble, non_blocking=non_blocking)
         self.y.copy_(y, non_blocking=non_blocking)
 
+    def check_peers(self):
+        """Raise if a peer-memory barrier gave up waiting for another rank (synchronises the device)."""
+        if self.p2p is not None and int(self.p2p["timed_out"].item()) != 0:
+            raise _lib.RcError("a rank did not reach the gradient-exchange barrier within 10 s")
+
     def prefetch(self, x, ensemble, y):
         """Start the host -> device copy of the NEXT batch (pinned host tensors) on the copy stream; it overlaps the
         step that is running.  `take_prefetched` moves it into the step's inputs."""
@@ -284,6 +338,7 @@ class TrainEngine:
     @property
     def launches_per_step(self) -> int:
         """librc kernel launches per step (program mode: the one persistent kernel, plus AdamW's two under DP)."""
+        opt = 4 if self.p2p is not None else 2        # barrier, tick, sum + AdamW, barrier  |  tick, AdamW
         if self._prog is not None:
-            return 1 if self.world == 1 else 3
-        return int(self.kernels_per_step or 0) + 2
+            return 1 if self.world == 1 else 1 + opt
+        return int(self.kernels_per_step or 0) + opt
