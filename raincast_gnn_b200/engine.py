@@ -99,11 +99,14 @@ class TrainEngine:
         self._prog = None
         self._side = torch.cuda.Stream(device=dev)      # weight-gradient work overlaps the data-gradient chain
         # input prefetch: the next batch travels host -> staging buffers on a copy stream while the current step runs
+        # In graph mode the staging buffers are a second input set with its own captured graph (same kernels, same
+        # pool): taking the prefetched batch is a flip, not a copy.  Other modes copy device -> device.
         self._copy = torch.cuda.Stream(device=dev)
-        self._stage = None                              # (x, ensemble, y) staging buffers, allocated on first use
+        self._stage = None                              # (x, ensemble, y) of the set being filled, allocated on first use
         self._staged = torch.cuda.Event()               # the staged batch has landed
-        self._stage_free = torch.cuda.Event()           # the staged batch has been moved into the step's inputs
+        self._stage_free = torch.cuda.Event()           # the set being filled is no longer read by a running step
         self._has_staged = False
+        self._alt_graph = None                          # graph of the step reading the other input set
         self._graph = None
         self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
 
@@ -306,15 +309,27 @@ class TrainEngine:
             torch.cuda.current_stream(self.device).wait_event(self._staged)
 
     def take_prefetched(self):
-        """Move the prefetched batch into the step's static inputs (device -> device, on the current stream)."""
+        """Make the prefetched batch the step's input.  Graph mode: flip to the input set it was copied into (its own
+        graph is captured on first use); otherwise a device -> device copy on the current stream."""
         if not self._has_staged:
             raise _lib.RcError("take_prefetched without a prefetch")
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._staged)
+        self._has_staged = False
+        if self._graph is not None:
+            # the current inputs become the set the next prefetch fills, once the step that reads them has run
+            # (step() records _stage_free after its replay)
+            (self.x, self.ens, self.y), self._stage = self._stage, (self.x, self.ens, self.y)
+            self._graph, self._alt_graph = self._alt_graph, self._graph
+            if self._graph is None:
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, pool=self._alt_graph.pool()):
+                    self._fwd_bwd()
+            self._flipped = True
+            return
         for dst, src in zip((self.x, self.ens, self.y), self._stage):
             dst.copy_(src, non_blocking=True)
         self._stage_free.record(cur)
-        self._has_staged = False
 
     def step(self):
         """One training step on the batch in the static buffers; returns the device-resident loss (float64 [1])."""
@@ -329,6 +344,9 @@ class TrainEngine:
         else:
             if self._graph is not None:
                 self._graph.replay()
+                if getattr(self, "_flipped", False):      # the other input set may be refilled once this replay has run
+                    self._stage_free.record(torch.cuda.current_stream(self.device))
+                    self._flipped = False
             else:
                 self._fwd_bwd()
             self._optimizer()
