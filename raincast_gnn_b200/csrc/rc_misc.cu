@@ -80,8 +80,8 @@ extern "C" int rc_reduce_segments(const rc_reduce_seg* segs, int n_segs, void* s
     }
     for (int i = cnt; i < RC_REDUCE_MAX_SEGS; ++i) args.seg[i] = rc_reduce_seg{nullptr, nullptr, 0, 0, 0, 0.f, 0, 0, 0};
     if (max_n == 0) continue;
-    int gx = ceil_div(max_n, 256);
-    if (gx > 64) gx = 64;
+    int gx = ceil_div(max_n, 32);             // a CTA finishes 32 outputs per pass
+    if (gx > 2 * kNumSMs) gx = 2 * kNumSMs;
     if (recording()) {
       if (int e = record_op(OP_REDUCE, 0, dim3(gx, cnt), 0, &args, sizeof(args))) return e;
       continue;

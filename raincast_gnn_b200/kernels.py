@@ -143,11 +143,14 @@ def linear_bwd_data(dy, w, *, mask_pos=None, w_ld=None, w_col0=0, k=None):
 
 
 def choose_splits(red_len: int, out_rows: int, out_cols: int) -> int:
-    """Reduction splits for a weight-gradient GEMM: enough CTAs to fill the SMs, >= 2 slices of 32 each."""
+    """Reduction splits for a weight-gradient GEMM: enough CTAs to fill the SMs, down to ONE 32-long reduction slice
+    per CTA.  At the reference shape (976 rows) a slice costs a full global -> shared round trip (~3 us) whatever the
+    tile does with it, so the 31 slices run side by side instead of 2 per CTA: the step went from 430 us to 389 us
+    (the weight-gradient stream had become the critical path of backward)."""
     tiles = max(1, math.ceil(red_len / 32))
     out_tiles = math.ceil(out_rows / 64) * math.ceil(out_cols / 128)
     want = max(1, math.ceil(2 * _SM / out_tiles))
-    return int(max(1, min(want, tiles // 2 if tiles >= 2 else 1)))
+    return int(max(1, min(want, tiles)))
 
 
 class GradSink:
