@@ -207,7 +207,7 @@ typedef struct rc_gemm {
 int rc_gemm_row_tile(const rc_gemm* g);  /* the row tile the launch would use (for stats sizing)   */
 int rc_gemm_run(const rc_gemm* g, void* stream);
 
-/* BatchNorm1d training-mode statistics from the RC_EPI_BN_STATS tiles (Chan's parallel update in
+/* BatchNorm1d training-mode statistics from the RC_EPI_BN_STATS tiles (per-tile count / mean / M2 combined in
  * float64): mean[N], rstd[N] = 1/sqrt(var_biased + eps); running_mean/var updated with `momentum`
  * and the UNBIASED variance, num_batches_tracked += 1 (torch.nn.BatchNorm1d, models/gnn.py:23). */
 int rc_bn_stats_finalize(const float* stats, int row_tiles, int row_tile, int m, int n, float eps,

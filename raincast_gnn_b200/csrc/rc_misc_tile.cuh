@@ -66,16 +66,7 @@ struct AdamP {
 
 
 // ---------------------------------------------------------------------------- BatchNorm forward stats
-// block (32 columns, 8 tile strides); Chan's pairwise update in float64, merged in a fixed order.
-struct Moments { double n, mean, m2; };
-__device__ __forceinline__ void chan_merge(Moments& a, double nb, double mean_b, double m2_b) {
-  if (nb <= 0.0) return;
-  const double n = a.n + nb, delta = mean_b - a.mean;
-  a.mean += delta * (nb / n);
-  a.m2 += m2_b + delta * delta * (a.n * nb / n);
-  a.n = n;
-}
-
+// block (32 columns, 8 tile strides); per-tile (count, mean, M2) combined in float64 in a fixed order.
 __device__ __forceinline__ void bn_stats_fin_tile(const BnStatsFinP& p, const uint3 bid, const uint3 gdim) {
   const float* __restrict__ stats = p.stats;
   int row_tiles = p.row_tiles;
@@ -91,40 +82,74 @@ __device__ __forceinline__ void bn_stats_fin_tile(const BnStatsFinP& p, const ui
   long long* num_batches_tracked = p.num_batches_tracked;
   (void)bid; (void)gdim;
 
-  __shared__ double sh[8][3][33];
+  // Two passes instead of a chain of pairwise (Chan) merges: mean = sum_t cnt_t mean_t / M, then
+  // M2 = sum_t [M2_t + cnt_t (mean_t - mean)^2] - the same quantity in real arithmetic, float64 throughout, fixed
+  // summation order, and no dependent divide per tile (the merge chain made this kernel 9 us at 122 tiles, four times
+  // on the forward critical path).  A thread keeps its tiles' statistics in registers across both passes.
+  __shared__ double sh[8][33];
+  __shared__ double sh_mean[33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = bid.x * 32 + tx;
-  Moments acc = {0.0, 0.0, 0.0};
-  if (col < n)
-    // 16 tiles' statistics are loaded before the first merge: the merges are a dependent float64 chain, and with the
-    // loads inside it every tile cost one L2 round trip (10 us per call at 122 tiles - the whole forward waited on it)
-    for (int t0 = ty; t0 < row_tiles; t0 += 8 * 16) {
-      float mu[16], m2[16];
+  constexpr int kHold = 16;                        // tiles per thread kept in registers (8 * 16 = 128 tiles per pass)
+  float mu[kHold], m2[kHold];
+  double s = 0.0;
+  const bool in_regs = row_tiles <= 8 * kHold;
+  if (col < n) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int t = t0 + 8 * k;
-        if (t < row_tiles) {
-          mu[k] = __ldg(stats + (size_t)t * 2 * n + col);
-          m2[k] = __ldg(stats + (size_t)t * 2 * n + n + col);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int t = t0 + 8 * k;
-        if (t < row_tiles) chan_merge(acc, (double)min(row_tile, m - t * row_tile), (double)mu[k], (double)m2[k]);
+    for (int k = 0; k < kHold; ++k) {
+      const int t = ty + 8 * k;
+      mu[k] = 0.f; m2[k] = 0.f;
+      if (t < row_tiles) {
+        mu[k] = __ldg(stats + (size_t)t * 2 * n + col);
+        m2[k] = __ldg(stats + (size_t)t * 2 * n + n + col);
       }
     }
-  sh[ty][0][tx] = acc.n; sh[ty][1][tx] = acc.mean; sh[ty][2][tx] = acc.m2;
+#pragma unroll
+    for (int k = 0; k < kHold; ++k) {
+      const int t = ty + 8 * k;
+      if (t < row_tiles) s += (double)min(row_tile, m - t * row_tile) * (double)mu[k];
+    }
+    for (int t = ty + 8 * kHold; t < row_tiles; t += 8)
+      s += (double)min(row_tile, m - t * row_tile) * (double)__ldg(stats + (size_t)t * 2 * n + col);
+  }
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += sh[k][tx];
+    sh_mean[tx] = tot / (double)m;
+  }
+  __syncthreads();
+  const double mean = sh_mean[tx];
+  double q = 0.0;
+  if (col < n) {
+#pragma unroll
+    for (int k = 0; k < kHold; ++k) {
+      const int t = ty + 8 * k;
+      if (t < row_tiles) {
+        const double d = (double)mu[k] - mean;
+        q += (double)m2[k] + (double)min(row_tile, m - t * row_tile) * d * d;
+      }
+    }
+    for (int t = ty + 8 * kHold; t < row_tiles; t += 8) {
+      const double d = (double)__ldg(stats + (size_t)t * 2 * n + col) - mean;
+      q += (double)__ldg(stats + (size_t)t * 2 * n + n + col) + (double)min(row_tile, m - t * row_tile) * d * d;
+    }
+  }
+  (void)in_regs;
+  sh[ty][tx] = q;
   __syncthreads();
   if (ty == 0 && col < n) {
-    Moments tot = {0.0, 0.0, 0.0};
-    for (int k = 0; k < 8; ++k) chan_merge(tot, sh[k][0][tx], sh[k][1][tx], sh[k][2][tx]);
-    const double var_b = tot.m2 / (double)m;
-    mean_out[col] = (float)tot.mean;
+    double tot_m2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot_m2 += sh[k][tx];
+    const double var_b = tot_m2 / (double)m;
+    mean_out[col] = (float)mean;
     rstd_out[col] = (float)(1.0 / sqrt(var_b + (double)eps));
-    if (running_mean != nullptr) running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)tot.mean;
+    if (running_mean != nullptr) running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)mean;
     if (running_var != nullptr) {
-      const float var_u = (float)(tot.m2 / (double)(m > 1 ? m - 1 : 1));
+      const float var_u = (float)(tot_m2 / (double)(m > 1 ? m - 1 : 1));
       running_var[col] = (1.0f - momentum) * running_var[col] + momentum * var_u;
     }
   }
