@@ -27,6 +27,35 @@ inline int check_launch(const char* what) {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Programmatic dependent launch.  A training step at the reference shape is a chain of ~50 dependent kernels of a few
+// microseconds each; between two of them the GPU idles for the launch latency of the second.  Every kernel of the step
+// therefore (a) is launched with programmaticStreamSerializationAllowed, so that its CTAs may be scheduled while the
+// kernel before it in the stream is still running, and (b) starts with pdl_entry(): griddepcontrol.wait blocks until
+// that kernel has completed and its writes are visible (nothing is read or written before it), and
+// griddepcontrol.launch_dependents lets the NEXT kernel's launch start as soon as all CTAs of this one are resident.
+// RC_PDL=0 turns the launch attribute off (the device-side instructions are then no-ops).
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename P>
+inline void launch_pdl(void (*kernel)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const P& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

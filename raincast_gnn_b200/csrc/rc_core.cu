@@ -1,11 +1,20 @@
 // Library-wide state: error text, version, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "rc_common.cuh"
 
 namespace rc {
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("RC_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;

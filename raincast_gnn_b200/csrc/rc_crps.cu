@@ -8,23 +8,28 @@
 namespace rc {
 
 __global__ void __launch_bounds__(kCrpsThreads) crps_count_kernel(const CrpsCountP p) {
+  pdl_entry();
   crps_count_tile(p, blockIdx, gridDim);
 }
 
 template <int WIDTH>
 __global__ void __launch_bounds__(kCrpsThreads) crps_main_kernel(const CrpsMainP p) {
+  pdl_entry();
   crps_main_tile<WIDTH>(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) crps_final_kernel(const CrpsFinalP p) {
+  pdl_entry();
   crps_final_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) postprocess_fwd_kernel(const PostFwdP p) {
+  pdl_entry();
   post_fwd_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) postprocess_bwd_kernel(const PostBwdP p) {
+  pdl_entry();
   post_bwd_tile(p, blockIdx, gridDim);
 }
 
@@ -57,16 +62,16 @@ extern "C" int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred,
     if (int e = record_op(OP_CRPS_MAIN, kind, dim3(blocks), 0, &pm, sizeof(pm))) return e;
     return record_op(OP_CRPS_FINAL, 0, dim3(1), 0, &pf, sizeof(pf));
   }
-  crps_count_kernel<<<ncnt, kCrpsThreads, 0, s>>>(pc);
+  launch_pdl(crps_count_kernel, dim3(ncnt), dim3(kCrpsThreads), 0, s, pc);
   if (int e = check_launch("crps_count_kernel")) return e;
   switch (kind) {
-    case 0: crps_main_kernel<2><<<blocks, kCrpsThreads, 0, s>>>(pm); break;
-    case 1: crps_main_kernel<3><<<blocks, kCrpsThreads, 0, s>>>(pm); break;
-    case 2: crps_main_kernel<4><<<blocks, kCrpsThreads, 0, s>>>(pm); break;
-    default: crps_main_kernel<5><<<blocks, kCrpsThreads, 0, s>>>(pm); break;
+    case 0: launch_pdl(crps_main_kernel<2>, dim3(blocks), dim3(kCrpsThreads), 0, s, pm); break;
+    case 1: launch_pdl(crps_main_kernel<3>, dim3(blocks), dim3(kCrpsThreads), 0, s, pm); break;
+    case 2: launch_pdl(crps_main_kernel<4>, dim3(blocks), dim3(kCrpsThreads), 0, s, pm); break;
+    default: launch_pdl(crps_main_kernel<5>, dim3(blocks), dim3(kCrpsThreads), 0, s, pm); break;
   }
   if (int e = check_launch("crps_main_kernel")) return e;
-  crps_final_kernel<<<1, 256, 0, s>>>(pf);
+  launch_pdl(crps_final_kernel, dim3(1), dim3(256), 0, s, pf);
   return check_launch("crps_final_kernel");
 }
 

@@ -10,12 +10,14 @@
 namespace rc {
 
 __global__ void __launch_bounds__(kDsThreads) deepsets_pool_fwd_kernel(const DsFwdP p) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   ds_fwd_tile(p, blockIdx, gridDim, smem);
 }
 
 template <int KQ>
 __global__ void __launch_bounds__(kDsThreads) deepsets_pool_bwd_kernel(const DsBwdP p) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   ds_bwd_tile<KQ>(p, blockIdx, gridDim, smem);
 }
@@ -45,7 +47,7 @@ extern "C" int rc_deepsets_pool_fwd(const float* ens, const float* w1, const flo
   dim3 grid(gx, ceil_div(hidden, kDsCols));
   const DsFwdP p{ens, w1, b1, pooled, num_nodes, members, feats, hidden, f4};
   if (recording()) return record_op(OP_DS_FWD, 0, grid, smem, &p, sizeof(p));
-  deepsets_pool_fwd_kernel<<<grid, kDsThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(deepsets_pool_fwd_kernel, grid, dim3(kDsThreads), smem, static_cast<cudaStream_t>(stream), p);
   return check_launch("deepsets_pool_fwd_kernel");
 }
 
@@ -77,7 +79,7 @@ static int ds_bwd_launch(const float* ens, const float* w1, const float* b1, con
   dim3 grid(ds_bwd_blocks(m), ceil_div(hidden, kDsCols));
   const DsBwdP p{ens, w1, b1, d_pooled, partials, m, members, feats, hidden, bf16_operands};
   if (recording()) return record_op(OP_DS_BWD, KQ, grid, smem, &p, sizeof(p));
-  deepsets_pool_bwd_kernel<KQ><<<grid, kDsThreads, smem, s>>>(p);
+  launch_pdl(deepsets_pool_bwd_kernel<KQ>, grid, dim3(kDsThreads), smem, s, p);
   return check_launch("deepsets_pool_bwd_kernel");
 }
 

@@ -17,38 +17,47 @@ namespace rc {
 
 template <int RM, int AL, int BL, int kRK>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmP p) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   gemm_tile<RM, AL, BL, kRK>(p, blockIdx, smem);
 }
 
+// `stages`: 2 when a CTA walks more than one reduction slice (double buffering), else 1.  The single-slice GEMMs of
+// the reference-shape step then take 72 KB instead of 143 KB: three CTAs fit an SM, so the CTAs of the next kernel in
+// the chain can already be resident (programmatic dependent launch) while this one is still running.
 template <int RM, int AL, int BL, int kRK>
-static size_t gemm_smem_bytes() {
+static size_t gemm_smem_bytes(int stages) {
   constexpr int kPadK = kRK + 4;
   constexpr int BM = 8 * RM;
   constexpr int SA = (AL == RC_A_ROW) ? kPadK : (BM + 4);
   constexpr int A_ROWS = (AL == RC_A_ROW) ? BM : kRK;
   constexpr int SB = (BL == RC_B_COL) ? kPadK : kBN;
   constexpr int B_ROWS = (BL == RC_B_COL) ? kBN : kRK;
-  size_t tiles = (size_t)2 * (A_ROWS * SA + B_ROWS * SB) * sizeof(float);
+  size_t tiles = (size_t)(2 * A_ROWS * SA + stages * B_ROWS * SB) * sizeof(float);    // A keeps both stages: B follows them
   size_t epi = (size_t)17 * kBN * sizeof(float);
   size_t cs = (size_t)kRK * BM * sizeof(float);
+  size_t part = (RM == 1 && kRK == 128 && AL == RC_A_ROW) ? (size_t)8 * 8 * kBN * sizeof(float) : 0;   // warp-split partials
   size_t need = tiles > epi ? tiles : epi;
-  return need > cs ? need : cs;
+  need = need > cs ? need : cs;
+  return need > part ? need : part;
 }
 
 template <int RM, int AL, int BL, int kRK>
 static int gemm_launch(const GemmP& p, dim3 grid, cudaStream_t s) {
   static bool attr_set = false;
-  const size_t smem = gemm_smem_bytes<RM, AL, BL, kRK>();
+  const int slices = p.tiles1 + p.tiles2;
+  const int per_cta = p.g.splits > 1 ? ceil_div(slices, p.g.splits) : slices;
+  const size_t smem = gemm_smem_bytes<RM, AL, BL, kRK>(per_cta > 1 ? 2 : 1);
   if (recording()) {
     if (RM > 4) return fail(RC_ERR_ARG, "rc_gemm_run: this tile shape is not part of the step program");
     return record_op(OP_GEMM, RM | (AL << 4) | (BL << 5) | ((kRK == 128) << 6), grid, smem, &p, sizeof(p));
   }
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_kernel<RM, AL, BL, kRK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm_kernel<RM, AL, BL, kRK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)gemm_smem_bytes<RM, AL, BL, kRK>(2));
     attr_set = true;
   }
-  gemm_kernel<RM, AL, BL, kRK><<<grid, kGemmThreads, smem, s>>>(p);
+  launch_pdl(gemm_kernel<RM, AL, BL, kRK>, grid, dim3(kGemmThreads), smem, s, p);
   return check_launch("gemm_kernel");
 }
 

@@ -13,16 +13,19 @@ namespace rc {
 
 template <int CH>
 __global__ void __launch_bounds__(kGineThreads) gine_aggr_fwd_kernel(const GineFwdP p) {
+  pdl_entry();
   gine_fwd_tile<CH>(p, blockIdx, gridDim);
 }
 
 template <int CH>
 __global__ void __launch_bounds__(kGineThreads) gine_aggr_bwd_kernel(const GineBwdP p) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   gine_bwd_tile<CH>(p, blockIdx, gridDim, smem);
 }
 
 __global__ void __launch_bounds__(256) gine_bwd_finalize_kernel(const GineFinP p) {
+  pdl_entry();
   gine_fin_tile(p, blockIdx, gridDim);
 }
 
@@ -46,10 +49,10 @@ extern "C" int rc_gine_aggr_fwd(const float* x, const int32_t* rowptr, const int
   const GineFwdP p{x, rowptr, col, attr, w_edge, b_edge, eps, h, num_nodes, hidden, sh.lpr};
   if (recording()) return record_op(OP_GINE_FWD, sh.ch, dim3(grid), 0, &p, sizeof(p));
   switch (sh.ch) {
-    case 1: gine_aggr_fwd_kernel<1><<<grid, kGineThreads, 0, s>>>(p); break;
-    case 2: gine_aggr_fwd_kernel<2><<<grid, kGineThreads, 0, s>>>(p); break;
-    case 3: gine_aggr_fwd_kernel<3><<<grid, kGineThreads, 0, s>>>(p); break;
-    default: gine_aggr_fwd_kernel<4><<<grid, kGineThreads, 0, s>>>(p); break;
+    case 1: launch_pdl(gine_aggr_fwd_kernel<1>, dim3(grid), dim3(kGineThreads), 0, s, p); break;
+    case 2: launch_pdl(gine_aggr_fwd_kernel<2>, dim3(grid), dim3(kGineThreads), 0, s, p); break;
+    case 3: launch_pdl(gine_aggr_fwd_kernel<3>, dim3(grid), dim3(kGineThreads), 0, s, p); break;
+    default: launch_pdl(gine_aggr_fwd_kernel<4>, dim3(grid), dim3(kGineThreads), 0, s, p); break;
   }
   return check_launch("gine_aggr_fwd_kernel");
 }
@@ -88,7 +91,7 @@ extern "C" int rc_gine_aggr_bwd(const float* g, const float* x, const int32_t* t
 #define RC_LAUNCH_BWD(CHV)                                                                                                  \
   do {                                                                                                                      \
     if (smem > 48 * 1024) cudaFuncSetAttribute(gine_aggr_bwd_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    gine_aggr_bwd_kernel<CHV><<<grid, kGineThreads, smem, s>>>(p);                                                         \
+    launch_pdl(gine_aggr_bwd_kernel<CHV>, dim3(grid), dim3(kGineThreads), smem, s, p);                                                         \
   } while (0)
   switch (sh.ch) {
     case 1: RC_LAUNCH_BWD(1); break;
@@ -106,6 +109,6 @@ extern "C" int rc_gine_aggr_bwd_finalize(const float* partials, int nblocks, int
   const int grid = ceil_div(2 * hidden, 32) + 1;
   const GineFinP p{partials, nblocks, hidden, d_w, d_b, d_eps};
   if (recording()) return record_op(OP_GINE_FIN, 0, dim3(grid), 0, &p, sizeof(p));
-  gine_bwd_finalize_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(gine_bwd_finalize_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("gine_bwd_finalize_kernel");
 }

@@ -7,26 +7,32 @@
 namespace rc {
 
 __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const BnStatsFinP p) {
+  pdl_entry();
   bn_stats_fin_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) bn_eval_prepare_kernel(const BnEvalP p) {
+  pdl_entry();
   bn_eval_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const BnBwdFinP p) {
+  pdl_entry();
   bn_bwd_fin_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) reduce_segments_kernel(const ReduceP p) {
+  pdl_entry();
   reduce_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(32) adamw_tick_kernel(const AdamTickP p) {
+  pdl_entry();
   adamw_tick_tile(p, blockIdx, gridDim);
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamP p) {
+  pdl_entry();
   adamw_tile(p, blockIdx, gridDim);
 }
 
@@ -42,7 +48,7 @@ extern "C" int rc_bn_stats_finalize(const float* stats, int row_tiles, int row_t
   const BnStatsFinP p{stats, row_tiles, row_tile, m, n, eps, momentum, mean, rstd, running_mean, running_var,
                       reinterpret_cast<long long*>(num_batches_tracked)};
   if (recording()) return record_op(OP_BN_STATS_FIN, 0, dim3(ceil_div(n, 32)), 0, &p, sizeof(p));
-  bn_stats_finalize_kernel<<<ceil_div(n, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(bn_stats_finalize_kernel, dim3(ceil_div(n, 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("bn_stats_finalize_kernel");
 }
 
@@ -62,7 +68,7 @@ extern "C" int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int 
     return fail(RC_ERR_ARG, "rc_bn_bwd_finalize: bad argument");
   const BnBwdFinP p{stats, row_tiles, m, n, batch_stats, gamma, mean, rstd, d_gamma, d_beta, c0, c1, c2};
   if (recording()) return record_op(OP_BN_BWD_FIN, 0, dim3(ceil_div(n, 32)), 0, &p, sizeof(p));
-  bn_bwd_finalize_kernel<<<ceil_div(n, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(n, 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("bn_bwd_finalize_kernel");
 }
 
@@ -86,7 +92,7 @@ extern "C" int rc_reduce_segments(const rc_reduce_seg* segs, int n_segs, void* s
       if (int e = record_op(OP_REDUCE, 0, dim3(gx, cnt), 0, &args, sizeof(args))) return e;
       continue;
     }
-    reduce_segments_kernel<<<dim3(gx, cnt), 256, 0, static_cast<cudaStream_t>(stream)>>>(args);
+    launch_pdl(reduce_segments_kernel, dim3(gx, cnt), dim3(256), 0, static_cast<cudaStream_t>(stream), args);
     if (int e = check_launch("reduce_segments_kernel")) return e;
   }
   return RC_OK;
@@ -105,9 +111,9 @@ extern "C" int rc_adamw_step(float* param, const float* grad, float* exp_avg, fl
     if (int e = record_op(OP_ADAMW_TICK, 0, dim3(1), 0, &pt, sizeof(pt))) return e;
     return n == 0 ? RC_OK : record_op(OP_ADAMW, 0, dim3((int)blocks), 0, &pa, sizeof(pa));
   }
-  adamw_tick_kernel<<<1, 32, 0, s>>>(pt);
+  launch_pdl(adamw_tick_kernel, dim3(1), dim3(32), 0, s, pt);
   if (int e = check_launch("adamw_tick_kernel")) return e;
   if (n == 0) return RC_OK;
-  adamw_kernel<<<(int)blocks, 256, 0, s>>>(pa);
+  launch_pdl(adamw_kernel, dim3((int)blocks), dim3(256), 0, s, pa);
   return check_launch("adamw_kernel");
 }

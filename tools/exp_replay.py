@@ -1,5 +1,6 @@
+"""Graph-replay time of the reference-shape step (B=8), back to back: python tools/exp_replay.py [label]"""
 import os, sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench as B
 from raincast_gnn_b200.engine import TrainEngine
 from raincast_gnn_b200.graph import build_station_graph
@@ -18,4 +19,4 @@ a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True
 a.record()
 for _ in range(200): eng._graph.replay()
 c.record(); c.synchronize()
-print(os.environ.get("RC_EXP", "base"), "graph replay %.1f us, launches %d" % (a.elapsed_time(c) / 200 * 1e3, eng.kernels_per_step))
+print(sys.argv[1] if len(sys.argv) > 1 else "", "graph replay %.1f us, launches %d" % (a.elapsed_time(c) / 200 * 1e3, eng.kernels_per_step))
