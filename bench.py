@@ -303,8 +303,9 @@ def run_b200(args):
     line = {"metric": "station-graphs/sec train (fwd+bwd+CRPS+AdamW)", "value": value, "unit": "graphs/s", "n_gpus": world,
             "steps": K_steps, "warmup": W, "ms_per_step": ms_dev / K_steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": f"dp{world} (dates sharded; per step one exchange of {eng.n_params} fp32 gradients: " +
-                                      ("summed from NVLink peer memory inside the AdamW kernel)" if eng.p2p is not None else "one NCCL all-reduce)"),
+            "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": (f"dp{world} (dates sharded; per step one exchange of {eng.n_params} fp32 gradients: " +
+                                       ("summed from NVLink peer memory inside the AdamW kernel)" if eng.p2p is not None else "one NCCL all-reduce)"))
+                                      if world > 1 else "single GPU (dates would be sharded rank::world; no gradient exchange)",
                        "timing": "per-step CUDA events on the launch stream; 256 MiB L2 flush between timed steps, outside the events; max over ranks",
                        "cuda_graph": True, "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
