@@ -44,6 +44,42 @@ constexpr int kDsMemberChunk = 16;
 
 // ---------------------------------------------------------------------------------------- forward
 // dynamic smem: Ws[F4][128] | bias[128] | Es[8 warps][kDsMemberChunk][F4]
+// idx / d for 0 <= idx < 2^20, 0 < d < 2^10 through one float multiply (inv = 1.0f / d): (idx + 0.5) / d is at least
+// 0.5 / d away from an integer, far more than the rounding error of the product.
+__device__ __forceinline__ int fast_div(int idx, float inv) { return __float2int_rd(((float)idx + 0.5f) * inv); }
+
+// W1 chunk [ncols][feats] (contiguous in HBM) -> shared [k][col], zero padded to fp x kDsCols.  Coalesced, eight loads
+// in flight per thread before the first store: a thread walking its own weight row k by k paid one L2 round trip per
+// element (this staging was 10 us of the 28 us pool backward at the reference shape).
+__device__ __forceinline__ void stage_w1(float* Ws, const float* __restrict__ w1, int c0, int hidden, int feats, int fp, int bf16) {
+  const int ncols = max(0, min(kDsCols, hidden - c0));
+  const int total = ncols * feats;
+  const float inv_feats = 1.0f / (float)feats;
+  const float* __restrict__ src = w1 + (size_t)c0 * feats;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * kDsThreads) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = i0 + u * kDsThreads;
+      v[u] = idx < total ? __ldg(src + idx) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = i0 + u * kDsThreads;
+      if (idx < total) {
+        const int col = fast_div(idx, inv_feats), k = idx - col * feats;
+        Ws[k * kDsCols + col] = round_operand(v[u], bf16);
+      }
+    }
+  }
+  for (int idx = threadIdx.x; idx < (fp - feats) * kDsCols; idx += kDsThreads) Ws[feats * kDsCols + idx] = 0.f;      // k padding
+  const int pad = kDsCols - ncols;
+  for (int idx = threadIdx.x; idx < feats * pad; idx += kDsThreads) {                                                // column padding
+    const int k = idx / pad;
+    Ws[k * kDsCols + ncols + (idx - k * pad)] = 0.f;
+  }
+}
+
 __device__ __forceinline__ void ds_fwd_tile(const DsFwdP& p, const uint3 bid, const uint3 gdim, float* smem) {
   const float* __restrict__ ens = p.ens;
   const float* __restrict__ w1 = p.w1;
@@ -61,14 +97,12 @@ __device__ __forceinline__ void ds_fwd_tile(const DsFwdP& p, const uint3 bid, co
   float* Es_all = bias + kDsCols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = bid.y * kDsCols;
-  // W1 chunk, transposed to [k][col]: thread <-> column, walks its own weight row
-  for (int j = tid; j < kDsCols; j += kDsThreads) {
-    const int col = c0 + j;
-    for (int k = 0; k < f4; ++k) Ws[k * kDsCols + j] = (col < hidden && k < feats) ? __ldg(w1 + (size_t)col * feats + k) : 0.f;
-    bias[j] = col < hidden ? __ldg(b1 + col) : 0.f;
-  }
+  // W1 chunk, transposed to [k][col]
+  stage_w1(Ws, w1, c0, hidden, feats, f4, 0);
+  for (int j = tid; j < kDsCols; j += kDsThreads) bias[j] = c0 + j < hidden ? __ldg(b1 + c0 + j) : 0.f;
   __syncthreads();
   float* Es = Es_all + warp * kDsMemberChunk * f4;
+  const float inv_feats = 1.0f / (float)feats;
   const float4 bv = ld4(bias + 4 * lane);
   const int kq = f4 >> 2;
   for (int node = bid.x * kDsWarps + warp; node < m; node += gdim.x * kDsWarps) {
@@ -80,9 +114,18 @@ __device__ __forceinline__ void ds_fwd_tile(const DsFwdP& p, const uint3 bid, co
       // stage cnt member rows (contiguous in HBM) into the padded [cnt][f4] layout
       const int total = cnt * feats;
       const float* s2 = src + (size_t)e0 * feats;
-      for (int idx = lane; idx < total; idx += 32) {
-        const int e = idx / feats, k = idx - e * feats;
-        Es[e * f4 + k] = __ldg(s2 + idx);
+      for (int i0 = lane; i0 < total; i0 += 4 * 32) {          // four loads in flight before the first store
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = i0 + 32 * u < total ? __ldg(s2 + i0 + 32 * u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = i0 + 32 * u;
+          if (idx < total) {
+            const int e = fast_div(idx, inv_feats), k = idx - e * feats;
+            Es[e * f4 + k] = v[u];
+          }
+        }
       }
       for (int idx = lane; idx < kDsMemberChunk * (f4 - feats); idx += 32) {     // zero the k padding
         const int e = idx / (f4 - feats), k = feats + idx - e * (f4 - feats);
@@ -167,12 +210,8 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
   float* dh = Es + ROWS * FP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = bid.y * kDsCols;
-  for (int j = tid; j < kDsCols; j += kDsThreads) {
-    const int col = c0 + j;
-    for (int k = 0; k < FP; ++k)
-      Ws[k * kDsCols + j] = (col < hidden && k < feats) ? round_operand(__ldg(w1 + (size_t)col * feats + k), bf16_operands) : 0.f;
-    bias[j] = col < hidden ? __ldg(b1 + col) : 0.f;
-  }
+  stage_w1(Ws, w1, c0, hidden, feats, FP, bf16_operands);
+  for (int j = tid; j < kDsCols; j += kDsThreads) bias[j] = c0 + j < hidden ? __ldg(b1 + c0 + j) : 0.f;
   const float4 bv_dummy = make_float4(0.f, 0.f, 0.f, 0.f);
   (void)bv_dummy;
   float dwacc[4 * KQ];
@@ -187,9 +226,17 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
     const int nrows = (int)min((long long)ROWS, total_rows - row0);
     // stage the tile (contiguous floats) into [64][FP], zero padded
     const float* src = ens + (size_t)row0 * feats;
-    for (int idx = tid; idx < ROWS * FP; idx += kDsThreads) {
-      const int r = idx / FP, k = idx - r * FP;
-      Es[idx] = (r < nrows && k < feats) ? round_operand(__ldg(src + (size_t)r * feats + k), bf16_operands) : 0.f;
+    {
+      constexpr int kIt = ROWS * FP / kDsThreads;            // all loads of the tile in flight before the first store
+      float v[kIt];
+#pragma unroll
+      for (int u = 0; u < kIt; ++u) {
+        const int idx = tid + u * kDsThreads;
+        const int r = idx / FP, k = idx - r * FP;
+        v[u] = (r < nrows && k < feats) ? __ldg(src + (size_t)r * feats + k) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kIt; ++u) Es[tid + u * kDsThreads] = round_operand(v[u], bf16_operands);
     }
     __syncthreads();
     // phase 1
