@@ -170,6 +170,8 @@ int rc_gine_aggr_bwd_tiled(const float* g, const float* x, const rc_gine_tiles* 
 #define RC_EPI_RELU_RES 2   /* D = res[i,j] + relu(v); bits (optional) record v > 0        (models/gnn.py:44) */
 #define RC_EPI_BN_STATS 3   /* D = v; per row-tile column mean / M2 -> stats[tile][2][N]  (BatchNorm forward) */
 #define RC_EPI_MASK_POS 4   /* D = aux[i,j] > 0 ? v : 0                                     (ReLU backward)    */
+#define RC_EPI_ADD_RES 6    /* D = v + res[i,j]   (dim_red: the half of the Linear that only needs the batch's x runs
+                               early, off the critical path, and joins here; models/gnn.py:134-135)         */
 #define RC_EPI_BN_RELU_BWD 5 /* z = p2*(aux-p0)*p1 + p3; D = z > 0 ? v : 0; column partial sums of D and
                                D*(aux-p0)*p1 -> stats[tile][2][N]               (ReLU + BatchNorm backward)   */
 
@@ -191,7 +193,7 @@ typedef struct rc_gemm {
   float* d; int ldd;
   const float* bias; float bias_scale;
   int epi;                    /* RC_EPI_* */
-  const float* res; int ld_res;           /* RC_EPI_RELU_RES */
+  const float* res; int ld_res;           /* RC_EPI_RELU_RES, RC_EPI_ADD_RES */
   uint32_t* bits_out; int ld_bits_out;    /* RC_EPI_RELU / RC_EPI_RELU_RES (optional) */
   const float* e_aux; int ld_e_aux;       /* RC_EPI_MASK_POS, RC_EPI_BN_RELU_BWD */
   const float* e_p0; const float* e_p1; const float* e_p2; const float* e_p3;

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RC_B200_LIB") or os.path.join(_HERE, "csrc", "librc_b
 RC_A_ROW, RC_A_RED = 0, 1
 RC_B_COL, RC_B_RED = 0, 1
 RC_OP_NONE, RC_OP_BN_RELU, RC_OP_BITMASK, RC_OP_AFFINE2 = 0, 1, 2, 3
-RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_EPI_BN_STATS, RC_EPI_MASK_POS, RC_EPI_BN_RELU_BWD = 0, 1, 2, 3, 4, 5
+RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_EPI_BN_STATS, RC_EPI_MASK_POS, RC_EPI_BN_RELU_BWD, RC_EPI_ADD_RES = 0, 1, 2, 3, 4, 5, 6
 RC_LOSS_NORMAL, RC_LOSS_MIXED_NORMAL, RC_LOSS_MIXED, RC_LOSS_MIXED_U = 0, 1, 2, 3
 
 _fp = C.c_void_p

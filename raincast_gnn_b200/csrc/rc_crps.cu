@@ -18,6 +18,57 @@ __global__ void __launch_bounds__(kCrpsThreads) crps_main_kernel(const CrpsMainP
   crps_main_tile<WIDTH>(p, blockIdx, gridDim);
 }
 
+// Batches of at most 1024 nodes (every reference-shape batch: 976): count, value + gradient and the mean in ONE CTA -
+// the valid count and the loss sum are block reductions instead of two more kernels on the step's critical path.
+// Same per-node function, same 1/n_valid scaling of the gradient; the loss sum is taken in float64 in warp order.
+struct CrpsSmallP {
+  CrpsMainP m;
+  double* loss_out;
+  int* n_valid;
+};
+
+template <int WIDTH>
+__global__ void __launch_bounds__(1024) crps_small_kernel(const CrpsSmallP p) {
+  pdl_entry();
+  const CrpsMainP& a = p.m;
+  __shared__ int shc[32];
+  __shared__ double shl[32];
+  __shared__ int s_cnt;
+  const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+  const float yi = i < a.m ? a.y[i] : nanf("");
+  int c = __popc(__ballot_sync(0xffffffffu, !isnan(yi)));
+  if (lane == 0) shc[warp] = c;
+  __syncthreads();
+  if (warp == 0) {
+    int t = shc[lane];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_cnt = t;
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  const float inv_n = cnt > 0 ? 1.0f / (float)cnt : 0.0f;
+  float loss = 0.0f;
+  if (i < a.m) {
+    float row[WIDTH], g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < WIDTH; ++j) row[j] = a.pred[(size_t)i * WIDTH + j];
+    if (!isnan(yi)) loss = crps_node_k<WIDTH - 2>(row, yi, a.raw_input, a.u_fixed, a.xi, a.t, g);
+    if (a.d_pred != nullptr) {
+#pragma unroll
+      for (int j = 0; j < WIDTH; ++j) a.d_pred[(size_t)i * WIDTH + j] = g[j] * inv_n;
+    }
+  }
+  const double dl = warp_sum((double)loss);
+  if (lane == 0) shl[warp] = dl;
+  __syncthreads();
+  if (i == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 32; ++w) tot += shl[w];
+    p.loss_out[0] = cnt > 0 ? tot / (double)cnt : nan("");   // mean of an empty selection is NaN in torch too
+    p.n_valid[0] = cnt;
+  }
+}
+
 __global__ void __launch_bounds__(256) crps_final_kernel(const CrpsFinalP p) {
   pdl_entry();
   crps_final_tile(p, blockIdx, gridDim);
@@ -61,6 +112,16 @@ extern "C" int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred,
     if (int e = record_op(OP_CRPS_COUNT, 0, dim3(ncnt), 0, &pc, sizeof(pc))) return e;
     if (int e = record_op(OP_CRPS_MAIN, kind, dim3(blocks), 0, &pm, sizeof(pm))) return e;
     return record_op(OP_CRPS_FINAL, 0, dim3(1), 0, &pf, sizeof(pf));
+  }
+  if (m > 0 && m <= 1024) {
+    const CrpsSmallP ps{pm, loss_out, n_valid};
+    switch (kind) {
+      case 0: launch_pdl(crps_small_kernel<2>, dim3(1), dim3(1024), 0, s, ps); break;
+      case 1: launch_pdl(crps_small_kernel<3>, dim3(1), dim3(1024), 0, s, ps); break;
+      case 2: launch_pdl(crps_small_kernel<4>, dim3(1), dim3(1024), 0, s, ps); break;
+      default: launch_pdl(crps_small_kernel<5>, dim3(1), dim3(1024), 0, s, ps); break;
+    }
+    return check_launch("crps_small_kernel");
   }
   launch_pdl(crps_count_kernel, dim3(ncnt), dim3(kCrpsThreads), 0, s, pc);
   if (int e = check_launch("crps_count_kernel")) return e;

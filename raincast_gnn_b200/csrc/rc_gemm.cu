@@ -111,7 +111,7 @@ extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
   if (g->bits_out && g->b_layout != RC_B_COL) return fail(RC_ERR_ARG, "rc_gemm_run: bits_out needs the forward layout");
   if ((g->epi == RC_EPI_BN_STATS || g->epi == RC_EPI_BN_RELU_BWD) && !g->stats) return fail(RC_ERR_ARG, "rc_gemm_run: stats missing");
   if ((g->epi == RC_EPI_MASK_POS || g->epi == RC_EPI_BN_RELU_BWD) && !g->e_aux) return fail(RC_ERR_ARG, "rc_gemm_run: e_aux missing");
-  if (g->epi == RC_EPI_RELU_RES && !g->res) return fail(RC_ERR_ARG, "rc_gemm_run: res missing");
+  if ((g->epi == RC_EPI_RELU_RES || g->epi == RC_EPI_ADD_RES) && !g->res) return fail(RC_ERR_ARG, "rc_gemm_run: res missing");
   if (g->epi == RC_EPI_BN_RELU_BWD && (!g->e_p0 || !g->e_p1 || !g->e_p2 || !g->e_p3)) return fail(RC_ERR_ARG, "rc_gemm_run: BN vectors missing");
   if (g->splits > 1 && g->epi != RC_EPI_NONE) return fail(RC_ERR_ARG, "rc_gemm_run: split reduction only with RC_EPI_NONE");
   if (g->splits > 1 && g->bias) return fail(RC_ERR_ARG, "rc_gemm_run: split reduction cannot add a bias");

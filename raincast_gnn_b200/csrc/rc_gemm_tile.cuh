@@ -392,6 +392,8 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
         v = fmaxf(v, 0.f);
       } else if (g.epi == RC_EPI_RELU_RES) {
         v = (ok ? __ldg(g.res + (size_t)row * g.ld_res + col) : 0.f) + fmaxf(v, 0.f);
+      } else if (g.epi == RC_EPI_ADD_RES) {
+        v += ok ? __ldg(g.res + (size_t)row * g.ld_res + col) : 0.f;
       } else if (g.epi == RC_EPI_MASK_POS) {
         v = (ok && __ldg(g.e_aux + (size_t)row * g.ld_e_aux + col) > 0.f) ? v : 0.f;
       }

@@ -175,7 +175,7 @@ class TrainEngine:
     def _fwd_bwd_body(self):
         blk = self._blocks
         Pd, Gd = blk["ds"]
-        K.dimred_prepack(blk["dr"][0], self.feats)       # side stream, overlaps the DeepSets kernels
+        K.dimred_prepack(blk["dr"][0], self.feats, self.x)   # side stream, overlaps the DeepSets kernels
         emb, s_ds = K.deepsets_fwd(Pd, self.ens, bf16=(getattr(self.model.deepset, "compute_dtype", "fp32") == "bf16"))
         Pr, Gr = blk["dr"]
         node, s_dr = K.dimred_fwd(Pr, self.x, emb)

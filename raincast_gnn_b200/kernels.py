@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import (RC_A_RED, RC_A_ROW, RC_B_COL, RC_B_RED, RC_EPI_BN_RELU_BWD, RC_EPI_BN_STATS, RC_EPI_MASK_POS,
-                   RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_OP_AFFINE2, RC_OP_BITMASK, RC_OP_BN_RELU, RC_OP_NONE)
+                   RC_EPI_ADD_RES, RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_OP_AFFINE2, RC_OP_BITMASK, RC_OP_BN_RELU, RC_OP_NONE)
 
 BN_EPS = 1e-5          # torch.nn.BatchNorm1d defaults (models/gnn.py:23)
 BN_MOMENTUM = 0.1
@@ -246,12 +246,14 @@ def deepsets_bwd(P, saved, d_emb, G):
 
 
 # --------------------------------------------------------------------------------------------- dim_red
-def dimred_prepack(P, f):
-    """dim_red.weight is [H, F + H] with F = 35: neither half of a row starts on a 16-byte boundary, and the GEMM
-    falls back to scalar loads for the whole 128 x 163 operand (measured 12.4 us against 5.4 us at the reference
-    shape, forward and backward-data alike).  The engine calls this at the start of a step: two strided copies on the
-    side stream (they overlap the DeepSets kernels) split the weight into aligned halves wx [H, F padded to 4] and
-    we [H, H]; dimred_fwd / dimred_bwd pick them up.  The parameter itself keeps the reference layout."""
+def dimred_prepack(P, f, x=None):
+    """Start of a step, on the side stream (overlaps the DeepSets kernels; the engine calls it):
+    * dim_red.weight is [H, F + H] with F = 35: neither half of a row starts on a 16-byte boundary, and the GEMM falls
+      back to scalar loads for the whole 128 x 163 operand.  Two strided copies split the weight into aligned halves
+      wx [H, F padded to 4] and we [H, H]; the parameter itself keeps the reference layout.
+    * with `x` (the batch's node features): xw = x @ wx^T + bias - the half of the Linear that does not need the
+      DeepSets embedding - is computed here too, so that dimred_fwd on the critical path is one 128-long reduction
+      slice that adds xw in its epilogue instead of two slices."""
     if RECORD.active or SIDE.stream is None:
         return
     w = P["dimred_w"]
@@ -261,9 +263,15 @@ def dimred_prepack(P, f):
         fpad = (f + 3) // 4 * 4
         pack = P["_dimred_pack"] = {"wx": torch.zeros((n, fpad), dtype=torch.float32, device=w.device),
                                     "we": torch.empty((n, ldw - f), dtype=torch.float32, device=w.device), "f": f}
+    pack["xw"] = None
     with on_side(w):
         pack["wx"][:, :f].copy_(w.detach()[:, :f])
         pack["we"].copy_(w.detach()[:, f:])
+        if x is not None:
+            m = x.shape[0]
+            xw = _new((m, n), torch.float32, x.device)
+            gemm(m, n, f, operand(x, f), operand(pack["wx"], pack["wx"].shape[1]), xw, n, bias=P["dimred_b"])
+            pack["xw"] = xw
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
     pack["ready"] = ev
@@ -287,8 +295,11 @@ def dimred_fwd(P, x, emb):
     pack = _dimred_pack(P, f)
     if pack is not None:
         torch.cuda.current_stream().wait_event(pack["ready"])
-        gemm(m, n, f, operand(x, f), operand(pack["wx"], pack["wx"].shape[1]), y, n, bias=P["dimred_b"],
-             a2=emb, lda2=h_in, b2=pack["we"], ldb2=h_in, k2=h_in)
+        if pack.get("xw") is not None:
+            gemm(m, n, h_in, operand(emb, h_in), operand(pack["we"], h_in), y, n, epi=RC_EPI_ADD_RES, res=pack["xw"], ld_res=n)
+        else:
+            gemm(m, n, f, operand(x, f), operand(pack["wx"], pack["wx"].shape[1]), y, n, bias=P["dimred_b"],
+                 a2=emb, lda2=h_in, b2=pack["we"], ldb2=h_in, k2=h_in)
     else:
         gemm(m, n, f, operand(x, f), operand(w, ldw), y, n, bias=P["dimred_b"],
              a2=emb, lda2=h_in, b2=w.reshape(-1)[f:], ldb2=ldw, k2=h_in)

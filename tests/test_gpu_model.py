@@ -305,7 +305,9 @@ def test_engine_prefetch_matches_load_batch(dev):
 
 def test_step_program_matches_graph_mode(dev):
     """The persistent step program (one cooperative kernel) and the CUDA-graph schedule of separate kernels are the
-    same arithmetic: identical loss trajectories, parameters, Adam state and BatchNorm buffers after 4 steps."""
+    same arithmetic up to summation order (the graph schedule computes the x half of dim_red ahead of time and reduces
+    a small batch's CRPS in one CTA): first-step loss, gradients and BatchNorm buffers agree to rounding, and the
+    loss trajectories stay together over 4 AdamW steps."""
     from raincast_gnn_b200.engine import TrainEngine
     c, batch, _, sd = build_case("ref_mixed_u", dev)
     from raincast_gnn_b200.models import GNN
@@ -317,18 +319,25 @@ def test_step_program_matches_graph_mode(dev):
         eng = TrainEngine(model, batch.station_graph, batch.x.shape[0], c["em"], c["f"], lr=1e-3, mode=mode).capture()
         assert (eng._prog is not None) == (mode == "program")
         eng.load_batch(batch.x, batch.ensemble, batch.y)
-        traj = [float(eng.step().item()) for _ in range(4)]
+        traj = [float(eng.step().item())]
         torch.cuda.synchronize()
-        out[mode] = (traj, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, eng.exp_avg_sq.cpu().clone(),
-                     int(eng.step_count))
-    (t_g, sd_g, v_g, n_g), (t_p, sd_p, v_p, n_p) = out["graph"], out["program"]
+        grads1 = {k: v.detach().cpu().clone() for k, v in eng.grads.items()}
+        bn1 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if "running" in k}
+        traj += [float(eng.step().item()) for _ in range(3)]
+        torch.cuda.synchronize()
+        out[mode] = (traj, grads1, bn1, int(eng.step_count))
+    (t_g, g_g, bn_g, n_g), (t_p, g_p, bn_p, n_p) = out["graph"], out["program"]
     assert n_g == n_p == 4
-    assert rel_err(np.array(t_p), np.array(t_g)) < 1e-6
-    for k in sd_g:
-        # Adam's first steps move every weight by ~lr*sign(grad): rounding-level gradient differences on
-        # near-zero gradients become +-lr, i.e. up to a few 1e-4 of the tensor scale after 4 steps at lr 1e-3
-        assert rel_err(sd_p[k].numpy(), sd_g[k].numpy()) < 2e-3, k
-    assert rel_err(v_p.numpy(), v_g.numpy()) < 1e-3
+    assert rel_err(np.array(t_p[:1]), np.array(t_g[:1])) < 1e-6
+    for k in g_g:
+        # (the Linear in front of BatchNorm has an exactly-zero true bias gradient: rounding noise on both sides; a ReLU
+        #  unit within rounding of its threshold moves whole gradient tensors by up to ~3e-3 of their scale)
+        if not k.endswith("nn.0.bias"):
+            assert rel_err(g_p[k].numpy(), g_g[k].numpy()) < 5e-3, k
+    for k in bn_g:
+        assert rel_err(bn_p[k].numpy(), bn_g[k].numpy()) < 1e-5, k
+    # later steps: what Adam makes of rounding-level gradient differences (near-zero gradients move weights by +-lr)
+    assert rel_err(np.array(t_p), np.array(t_g)) < 2e-3
 
 
 @pytest.mark.parametrize("members", [11, 51])
