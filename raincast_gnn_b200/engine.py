@@ -107,6 +107,7 @@ class TrainEngine:
         self._stage_free = torch.cuda.Event()           # the set being filled is no longer read by a running step
         self._has_staged = False
         self._alt_graph = None                          # graph of the step reading the other input set
+        self._flipped = False                           # the running step reads a set that a prefetch will refill
         self._graph = None
         self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
 
@@ -344,7 +345,7 @@ class TrainEngine:
         else:
             if self._graph is not None:
                 self._graph.replay()
-                if getattr(self, "_flipped", False):      # the other input set may be refilled once this replay has run
+                if self._flipped:                         # the other input set may be refilled once this replay has run
                     self._stage_free.record(torch.cuda.current_stream(self.device))
                     self._flipped = False
             else:
