@@ -289,6 +289,7 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
     }
     __syncthreads();
     // phase 2
+#pragma unroll 4
     for (int r = 0; r < nrows; ++r) {
       const float d = dh[r * kDsCols + c_own];
       if (half == 0) dbacc += d;

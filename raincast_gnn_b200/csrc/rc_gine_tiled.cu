@@ -4,10 +4,11 @@
 // edge.  At ~30 edges per station that is 30x the compulsory traffic, and the plain warp-per-row kernels of
 // rc_gine.cu / rc_gine_wide.cu sit at the L2 -> SM throughput cap (profiles/r01_ncu_gine_aggr.txt).  Here one
 // persistent CTA per SM walks its share of the tiles through a two-buffer shared-memory pipeline:
-//   - producer warps (one per SM sub-partition) stage the rows a tile gathers (own rows + halo, ~2.5 rows per owned
+//   - eight producer warps (two per SM sub-partition) stage the rows a tile gathers (own rows + halo, ~2.5 rows per owned
 //     row on the config-4 graph, exactly 1.0 on batched reference graphs) and the tile's block of group / entry
 //     records with cp.async (global -> shared without registers, 16 bytes per lane) and signal an mbarrier when
-//     the copies have landed; the next tile is in flight while the consumers work on the current one
+//     the copies have landed; the next tile is in flight while the consumers work on the current one.  Forward tiles
+//     are handed out from a global counter (dynamic schedule), backward tiles round robin (reproducible partial sums)
 //   - consumer warps claim GROUPS of three neighbouring rows from a shared counter (groups with most edges first).
 //     Each distinct source row of the group is read from shared memory once and used by every row of the group that
 //     has an edge from it (2.2 edges per 512-byte read on config 4) - the shared-memory data pipe was the limiter of
