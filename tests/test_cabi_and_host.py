@@ -243,3 +243,37 @@ def test_station_tiles_edge_cases():
     tiles = G.build_tiles_host(empty.rowptr, empty.col, empty.attr, 8, 4096, 512)
     assert tiles.n_tiles == 0 and tiles.n_staged == 0
     assert G.tile_limits(100) is None and G.tile_limits(512) == G.tile_limits(128)
+
+
+def test_station_tiles_verifier_rejects_corruption():
+    """rc_gine_tiles_verify_host is the CPU check of the layout the tiled kernels walk: it must notice a wrong
+    attribute, a wrong staged offset, a row owned twice and a missing edge."""
+    coords = syn.station_coords(600, 120.0, seed=5)
+    ei, ea = G.radius_graph_from_coords(coords, syn.scaled_graph_radius(600, 120.0, 10.0))
+    sg = G.build_station_graph(ei, ea, 600)
+    tiles = G.build_tiles_host(sg.rowptr, sg.col, sg.attr, 64, 8192, 512)
+    tiles.verify(sg.rowptr, sg.col, sg.attr)
+    blocks = tiles.arrays["blocks"]
+    tbp = tiles.arrays["tile_blk_ptr"].numpy()
+    hdr = blocks[4 * tbp[0]: 4 * tbp[0] + 4].numpy()
+    ent0 = 4 * tbp[0] + (16 + 48 * int(hdr[2])) // 4            # first entry of the first tile
+
+    def corrupted(idx, value):
+        saved = int(blocks[idx])
+        blocks[idx] = value
+        try:
+            with pytest.raises(_lib.RcError):
+                tiles.verify(sg.rowptr, sg.col, sg.attr)
+        finally:
+            blocks[idx] = saved
+    rec = blocks[4 * tbp[0] + 4: 4 * tbp[0] + 16].numpy()      # group 0: {nodes, entry offset}{class counts}{degrees, self}
+    cnt = [0, rec[4] & 0xffff, (rec[4] >> 16) & 0xffff, rec[5] & 0xffff, (rec[5] >> 16) & 0xffff, rec[6] & 0xffff,
+           (rec[6] >> 16) & 0xffff, rec[7]]
+    cls = max(c for c in range(1, 8) if cnt[c])                 # class of group 0's last entry
+    last = ent0 + 4 * (sum(cnt) - 1)
+    k = [b for b in range(3) if cls & (1 << b)][0]
+    corrupted(last + 1 + k, int(blocks[last + 1 + k]) ^ 1)      # one attribute bit of a row that uses the entry
+    corrupted(ent0, int(blocks[ent0]) + 512 * 4096)                                   # staged offset out of range
+    corrupted(4 * tbp[0] + 4, int(blocks[4 * tbp[0] + 8]) if False else int(blocks[4 * tbp[0] + 5]))   # row 0 := row 1 (owned twice)
+    corrupted(4 * tbp[0] + 8, 0)                                                      # class counts zeroed: edges missing
+    tiles.verify(sg.rowptr, sg.col, sg.attr)                                          # restored
