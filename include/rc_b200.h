@@ -292,6 +292,15 @@ int rc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, void* stream);
 
+/* GPU-resident split (replaces the per-step PyG collate + 7 H2D copies of train.py:61-62,155-156 when
+ * the whole split fits in HBM: the reference's train split is ~0.7 GB).  x_all [n_dates][x_len], ens_all
+ * [n_dates][ens_len], y_all [n_dates][y_len] live on the device; `dates` (device int64 [n_batch]) selects the batch,
+ * which lands in the step's inputs x [n_batch][x_len], ens, y in the order given (= PyG's concatenation order for a
+ * static graph).  An index outside [0, n_dates) sets *bad = 1 and copies nothing for that slot. */
+int rc_gather_dates(const float* x_all, const float* ens_all, const float* y_all, const int64_t* dates, int n_batch,
+                    int n_dates, long long x_len, long long ens_len, long long y_len, float* x, float* ens, float* y,
+                    int32_t* bad, void* stream);
+
 /* Data-parallel step over NVLink peer memory (the reference, train.py:55-74,185, is single device):
  * every rank keeps its flat gradient where the other ranks of the box can read it, and
  *     rc_p2p_barrier(slot 0)  ->  rc_p2p_adamw_step  ->  rc_p2p_barrier(slot 1)

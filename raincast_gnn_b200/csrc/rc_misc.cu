@@ -36,9 +36,51 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamP p) {
   adamw_tile(p, blockIdx, gridDim);
 }
 
+// One batch of forecast dates out of a device-resident split: the three per-date blocks (node features, ensemble, targets)
+// of `n_batch` dates are copied into the step's static inputs by one launch; blockIdx.y = position in the batch.
+struct GatherDatesP {
+  const float* x_all; const float* ens_all; const float* y_all;
+  const long long* dates;
+  long long x_len, ens_len, y_len;     // floats per date
+  int n_dates;
+  float* x; float* ens; float* y;
+  int* bad;                            // set to 1 when a date index is out of range (the copy is skipped)
+};
+
+__global__ void __launch_bounds__(256) gather_dates_kernel(const GatherDatesP p) {
+  pdl_entry();
+  const int b = blockIdx.y;
+  const long long d = p.dates[b];
+  if (d < 0 || d >= p.n_dates) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(p.bad, 1);
+    return;
+  }
+  const long long total = p.x_len + p.ens_len + p.y_len;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    if (i < p.x_len) p.x[b * p.x_len + i] = __ldg(p.x_all + d * p.x_len + i);
+    else if (i < p.x_len + p.ens_len) p.ens[b * p.ens_len + (i - p.x_len)] = __ldg(p.ens_all + d * p.ens_len + (i - p.x_len));
+    else p.y[b * p.y_len + (i - p.x_len - p.ens_len)] = __ldg(p.y_all + d * p.y_len + (i - p.x_len - p.ens_len));
+  }
+}
+
 }  // namespace rc
 
 using namespace rc;
+
+extern "C" int rc_gather_dates(const float* x_all, const float* ens_all, const float* y_all, const int64_t* dates, int n_batch,
+                               int n_dates, long long x_len, long long ens_len, long long y_len, float* x, float* ens, float* y,
+                               int32_t* bad, void* stream) {
+  if (!x_all || !ens_all || !y_all || !dates || !x || !ens || !y || !bad || n_batch < 0 || n_dates < 0 || x_len < 0 || ens_len < 0 ||
+      y_len < 0)
+    return fail(RC_ERR_ARG, "rc_gather_dates: bad argument");
+  if (n_batch == 0) return RC_OK;
+  const long long total = x_len + ens_len + y_len;
+  long long gx = ceil_div_ll(total > 0 ? total : 1, 256);
+  if (gx > 2 * kNumSMs) gx = 2 * kNumSMs;
+  const GatherDatesP p{x_all, ens_all, y_all, reinterpret_cast<const long long*>(dates), x_len, ens_len, y_len, n_dates, x, ens, y, bad};
+  launch_pdl(gather_dates_kernel, dim3((int)gx, n_batch), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+  return check_launch("gather_dates_kernel");
+}
 
 extern "C" int rc_bn_stats_finalize(const float* stats, int row_tiles, int row_tile, int m, int n, float eps,
                                     float momentum, float* mean, float* rstd, float* running_mean, float* running_var,

@@ -286,6 +286,20 @@ class TrainEngine:
         self.ens.copy_(ensemble, non_blocking=non_blocking)
         self.y.copy_(y, non_blocking=non_blocking)
 
+    def load_dates(self, split, dates: torch.Tensor):
+        """Build the step's batch from a device-resident split (utils.dataset.DeviceSplit): `dates` is a device int64
+        tensor of B forecast-date indices; one gather kernel, no host copy."""
+        b = int(dates.numel())
+        n = split.num_stations
+        if b * n != self.m or split.x.shape[2] != self.feats or split.ensemble.shape[2] != self.members:
+            raise _lib.RcError(f"load_dates: {b} dates of {n} stations do not make the captured batch of {self.m} nodes")
+        if getattr(self, "_bad_date", None) is None:
+            self._bad_date = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().rc_gather_dates(split.x.data_ptr(), split.ensemble.data_ptr(), split.y.data_ptr(),
+                                              dates.data_ptr(), b, len(split), n * self.feats, n * self.members * self.feats, n,
+                                              self.x.data_ptr(), self.ens.data_ptr(), self.y.data_ptr(), self._bad_date.data_ptr(),
+                                              torch.cuda.current_stream(self.device).cuda_stream), "rc_gather_dates")
+
     def check_peers(self):
         """Raise if a peer-memory barrier gave up waiting for another rank (synchronises the device)."""
         if self.p2p is not None and int(self.p2p["timed_out"].item()) != 0:

@@ -27,7 +27,7 @@ from . import dp
 from .engine import TrainEngine
 from .models.gnn import GNN
 from .pyg_compat import DataLoader
-from .utils.dataset import EUPPBench, SyntheticEUPPBench
+from .utils.dataset import DeviceSplit, EUPPBench, SyntheticEUPPBench
 
 LOG = logging.getLogger("raincast_gnn_b200.train")
 
@@ -44,6 +44,8 @@ def parse_args(argv=None):
                      ("--max_epochs", dict(type=int, default=None))):
         ap.add_argument(flag, **kw)
     ap.add_argument("--engine", action="store_true", help="CUDA-graph training engine instead of autograd")
+    ap.add_argument("--resident", action="store_true",
+                    help="with --engine: keep the training split on the GPU and build batches there (no per-step collate / H2D)")
     return ap.parse_args(argv)
 
 
@@ -100,6 +102,16 @@ def run_epoch_engine(engine: TrainEngine, loader) -> float:
         done += 1
     del held
     return engine.loss_sum.item() / max(done, 1)
+
+
+def run_epoch_resident(engine: TrainEngine, split: DeviceSplit, batch_size: int, generator) -> float:
+    """One pass over a GPU-resident split: a device-side gather builds every batch."""
+    engine.loss_sum.zero_()
+    batches = split.epoch_batches(batch_size, generator=generator)
+    for dates in batches:
+        engine.load_dates(split, dates)
+        engine.step()
+    return engine.loss_sum.item() / max(len(batches), 1)
 
 
 @torch.no_grad()
@@ -163,12 +175,25 @@ def main(argv=None):
     else:
         optimizer = model.optimizer_class(model.parameters(), **model.optimizer_params)
 
+    resident = None
+    if args.resident:
+        if engine is None:
+            raise SystemExit("--resident needs --engine")
+        resident = DeviceSplit([fit_part[i] for i in range(len(fit_part))], device)
+        resident_rng = torch.Generator().manual_seed(args.seed + 1000 * rank)
+        LOG.info("training split resident on %s: %.1f MB", device,
+                 (resident.x.numel() + resident.ensemble.numel() + resident.y.numel()) * 4 / 1e6)
     os.makedirs(os.path.join(args.dir, "models"), exist_ok=True)
     target = os.path.join(args.dir, "models", f"run_{args.run_id}-best.ckpt")
     best, saved = float("inf"), None
     n_epochs = args.max_epochs or cfg["max_epochs"]
     for epoch in range(1, n_epochs + 1):
-        fit_loss = run_epoch_engine(engine, fit_loader) if engine is not None else run_epoch_autograd(model, fit_loader, optimizer, device)
+        if resident is not None:
+            fit_loss = run_epoch_resident(engine, resident, bs, resident_rng)
+        elif engine is not None:
+            fit_loss = run_epoch_engine(engine, fit_loader)
+        else:
+            fit_loss = run_epoch_autograd(model, fit_loader, optimizer, device)
         val_loss = validate(model, val_loader, device) if len(val_part) else float("nan")
         LOG.info("epoch %d/%d  [Train] Loss: %.6f  [Val] Loss: %.6f", epoch, n_epochs, fit_loss, val_loss)
         if rank == 0 and (val_loss < best or saved is None):

@@ -70,3 +70,35 @@ class EUPPBench:
 
     def __getitem__(self, i):
         return self.graphs[i]
+
+
+class DeviceSplit:
+    """A split held on the GPU: x [D, N, F], ensemble [D, N, Em, F], y [D, N] stacked over the forecast
+    dates of a dataset whose graphs share one static station graph.  `TrainEngine.load_dates(split, dates)` then builds
+    a batch with one gather kernel and no host work - the reference collates on the CPU main thread and issues seven
+    H2D copies per step (train.py:61-62,155-156)."""
+
+    def __init__(self, graphs, device):
+        graphs = list(graphs)
+        if not graphs:
+            raise ValueError("DeviceSplit needs at least one graph")
+        first = graphs[0]
+        for g in graphs:
+            if g.x.shape != first.x.shape or g.ensemble.shape != first.ensemble.shape:
+                raise ValueError("DeviceSplit needs graphs of one shape (a static station graph)")
+        self.x = torch.stack([g.x for g in graphs]).float().contiguous().to(device)
+        self.ensemble = torch.stack([g.ensemble for g in graphs]).float().contiguous().to(device)
+        self.y = torch.stack([g.y.reshape(-1) for g in graphs]).float().contiguous().to(device)
+        self.edge_index, self.edge_attr = first.edge_index, first.edge_attr
+        self.num_stations = first.x.shape[0]
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def epoch_batches(self, batch_size: int, generator=None, shuffle: bool = True):
+        """Device int64 index tensors of `batch_size` dates each (a ragged last batch is dropped: the captured step has
+        a fixed shape)."""
+        n = len(self)
+        order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+        order = order[: (n // batch_size) * batch_size].to(self.x.device)
+        return list(order.split(batch_size))

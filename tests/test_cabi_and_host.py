@@ -277,3 +277,20 @@ def test_station_tiles_verifier_rejects_corruption():
     corrupted(4 * tbp[0] + 4, int(blocks[4 * tbp[0] + 8]) if False else int(blocks[4 * tbp[0] + 5]))   # row 0 := row 1 (owned twice)
     corrupted(4 * tbp[0] + 8, 0)                                                      # class counts zeroed: edges missing
     tiles.verify(sg.rowptr, sg.col, sg.attr)                                          # restored
+
+
+def test_device_split_epoch_batches():
+    """DeviceSplit (utils/dataset.py) on the CPU: stacking, fixed-shape batches, ragged tail dropped, reproducible order."""
+    from raincast_gnn_b200.utils.dataset import DeviceSplit, SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=11, num_stations=7, members=3, feats=5)
+    split = DeviceSplit([ds[i] for i in range(len(ds))], "cpu")
+    assert split.x.shape == (11, 7, 5) and split.ensemble.shape == (11, 7, 3, 5) and split.y.shape == (11, 7) and len(split) == 11
+    assert torch.equal(split.x[4], ds[4].x) and torch.equal(split.ensemble[9], ds[9].ensemble)
+    b1 = split.epoch_batches(4, generator=torch.Generator().manual_seed(3))
+    b2 = split.epoch_batches(4, generator=torch.Generator().manual_seed(3))
+    assert len(b1) == 2 and all(b.numel() == 4 and b.dtype == torch.int64 for b in b1)
+    assert all(torch.equal(a, b) for a, b in zip(b1, b2))
+    assert len(set(torch.cat(b1).tolist())) == 8
+    assert torch.equal(torch.cat(split.epoch_batches(5, shuffle=False)), torch.arange(10))
+    with pytest.raises(ValueError):
+        DeviceSplit([], "cpu")

@@ -53,3 +53,49 @@ def test_training_reduces_the_loss(run_dir):
     eng.load_batch(batch.x, batch.ensemble, batch.y)
     losses = [float(eng.step().item()) for _ in range(30)]
     assert losses[-1] < 0.8 * losses[0]
+
+
+def test_resident_split_matches_host_batches(run_dir):
+    """GPU-resident split: rc_gather_dates builds the same batch as PyG-style collation + H2D, so the
+    loss trajectories are identical; an out-of-range date index is reported, not read."""
+    from raincast_gnn_b200 import _lib
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.pyg_compat import Batch
+    from raincast_gnn_b200.utils.dataset import DeviceSplit, SyntheticEUPPBench
+    cfg = json.load(open(os.path.join(run_dir, "params.json")))
+    dev = torch.device("cuda:0")
+    ds = SyntheticEUPPBench(n_dates=24)
+    split = DeviceSplit([ds[i] for i in range(len(ds))], dev)
+    order = [torch.tensor(o) for o in ([3, 17, 0, 9, 22, 5, 11, 8], [1, 2, 4, 6, 7, 10, 12, 13], [23, 21, 20, 19, 18, 16, 15, 14])]
+    trajs = []
+    for resident in (False, True):
+        torch.manual_seed(0)
+        model = GNN(35, cfg["gnn_hidden"], cfg["gnn_hidden"], cfg["gnn_layers"], torch.optim.AdamW, {"lr": 1e-3}, cfg["loss"],
+                    cfg["grad_u"], cfg["u"], cfg["xi"]).to(dev).train()
+        first = Batch.from_data_list([ds[int(i)] for i in order[0]])
+        eng = TrainEngine(model, first.station_graph, first.x.shape[0], 11, 35, lr=1e-3).capture()
+        traj = []
+        for dates in order:
+            if resident:
+                eng.load_dates(split, dates.to(dev))
+            else:
+                b = Batch.from_data_list([ds[int(i)] for i in dates])
+                eng.load_batch(b.x, b.ensemble, b.y)
+            traj.append(float(eng.step().item()))
+        trajs.append(traj)
+    assert trajs[0] == trajs[1]
+    eng.load_dates(split, torch.tensor([0, 1, 2, 3, 4, 5, 6, 24], device=dev))
+    torch.cuda.synchronize()
+    assert int(eng._bad_date) == 1
+    with pytest.raises(_lib.RcError):
+        eng.load_dates(split, torch.tensor([0, 1], device=dev))
+
+
+def test_train_cli_resident(run_dir):
+    from raincast_gnn_b200 import train as rc_train
+    ckpt = rc_train.main(["--leadtime", "24h", "--dir", run_dir, "--run_id", "1", "--synthetic", "40", "--max_epochs", "2", "--engine",
+                          "--resident"])
+    assert os.path.isfile(ckpt)
+    log = open(os.path.join(run_dir, "logs", "train_1.log")).read()
+    assert "resident on" in log and "[Train] Loss:" in log
