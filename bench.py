@@ -13,7 +13,9 @@ fp32): forward, CRPS, backward, gradient all-reduce (N > 1), AdamW.  Prints ONE 
            copy of x / ensemble / y (the next step's batch, prefetched on a copy stream while this step runs, as
            train.py does) and a D2H read of the loss
   roofline — the GINE aggregation forward kernel on the config-4 graph (100k nodes, 2 978 560 edges,
-           H=128): algorithmic bytes 2*M*H*4 + E*8 + (M+1)*4 + 8*H   / mean CUDA-event time
+           H=128): algorithmic bytes 2*M*H*4 + E*8 + (M+1)*4 + 8*H  (SURVEY.md 8d) / mean CUDA-event time;
+           `bwd` and `batched_reference_graphs` (4096 reference graphs in one batch) report the same for the
+           backward kernel and for the graph shape where HBM, not the SM, is the relevant bound
   cpu_baseline — the CPU oracle (reference modules' arithmetic, oracle/) timed on this box's host cores
 """
 from __future__ import annotations
@@ -178,12 +180,21 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- roofline leg
-def measure_aggregation(dev, iters: int = 20):
-    """GINE aggregation fwd (and bwd) on the config-4 graph; L2 is flushed between launches so x comes from HBM."""
-    from raincast_gnn_b200 import _lib, graph as G
+def measure_aggregation(dev, iters: int = 20, which: str = "config4"):
+    """GINE aggregation fwd (and bwd), L2 flushed between launches so x comes from HBM.
+    which = "config4": the 100k-node radius graph of SURVEY.md 8d (30 edges per row);
+    which = "ref4096": 4096 reference station graphs in one batch (499 712 nodes, 9.5 edges per row, block diagonal)."""
+    from raincast_gnn_b200 import graph as G
+    from raincast_gnn_b200 import kernels as K
     from raincast_gnn_b200.utils import synthetic as syn
-    n, h = 100_000, HIDDEN
-    ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
+    h = HIDDEN
+    if which == "config4":
+        n = 100_000
+        ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
+    else:
+        ei1, ea1, _, _ = static_graph(1)
+        n = 4096 * N_STATIONS
+        ei, ea = G.collate_static(ei1, ea1, N_STATIONS, 4096)
     sg = G.build_station_graph(ei, ea, n).to(dev)
     e = ei.shape[1]
     g = torch.Generator().manual_seed(0)
@@ -191,7 +202,6 @@ def measure_aggregation(dev, iters: int = 20):
     gout = torch.randn(n, h, generator=g).to(dev)
     w, b, eps = torch.randn(h, generator=g).to(dev), torch.randn(h, generator=g).to(dev), torch.zeros(1, device=dev)
     out = torch.empty_like(x)
-    from raincast_gnn_b200 import kernels as K
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sg.tiles(h)                    # the product path: station tiles (built once per graph, like the CSR)
 
@@ -325,6 +335,14 @@ def run_b200(args):
                                 "bwd": {"achieved": bb / (res["bwd"] * 1e-3) / 1e9, "algorithmic_bytes": bb,
                                         "us_per_launch": res["bwd"] * 1e3,
                                         "frac": bb / (res["bwd"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+            # the same kernels where HBM is the relevant bound: a large batch of reference station graphs
+            res2, bf2, bb2, n2, e2 = measure_aggregation(dev, iters=10, which="ref4096")
+            line["roofline"]["batched_reference_graphs"] = {
+                "workload": f"4096 reference graphs in one batch: {n2} nodes, {e2} edges, H=128",
+                "fwd": {"achieved": bf2 / (res2["fwd"] * 1e-3) / 1e9, "frac": bf2 / (res2["fwd"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "us_per_launch": res2["fwd"] * 1e3, "algorithmic_bytes": bf2},
+                "bwd": {"achieved": bb2 / (res2["bwd"] * 1e-3) / 1e9, "frac": bb2 / (res2["bwd"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "us_per_launch": res2["bwd"] * 1e3, "algorithmic_bytes": bb2}}
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     tr = json.load(f)
