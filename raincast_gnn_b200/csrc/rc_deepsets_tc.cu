@@ -50,6 +50,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// 32 lanes x 32 columns of the accumulator -> one column per register; completes at tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -57,8 +75,14 @@ __device__ __forceinline__ float to_tf32(float v) {
 }
 
 // dynamic shared memory (bytes), all 16-byte aligned:
-//   A_hi [chunks][128][16] | A_lo (fp32 mode) | B_hi | B_lo (fp32 mode) | staging [128*feats] fp32 | bias [128] | mbar | tmem ptr
-template <bool BF16>
+//   A_hi [chunks][128][16] | A_lo (fp32 mode) | B_hi | B_lo (fp32 mode) | staging [128*feats + 8] fp32 | bias [128] | mbar | tmem ptr
+// A tile's member rows are contiguous in HBM; they travel as 16-byte cp.async chunks of the aligned span that covers them
+// (the tile starts `mis` floats into the first chunk), issued for tile i+1 right after tile i has been converted, so the
+// HBM latency of the next tile hides behind the MMAs, the TMEM read-back and the pooling of the current one.
+// MEMBERS > 0 / KQ > 0: the member count / ceil(feats / 8) are compile-time (instantiated for the reference's ensembles of
+// 11 and 51 members and its 35 features): station boundaries in the pooling epilogue and the operand conversion are then
+// static - no per-column boundary test or branch, all shared-memory loads of a row in flight at once.  0 = any value.
+template <bool BF16, int MEMBERS, int KQ>
 __global__ void __launch_bounds__(kTcThreads)
 deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restrict__ w1, const float* __restrict__ b1,
                             float* __restrict__ pooled, int m, int members, int feats, int hidden, int nodes_per_tile,
@@ -72,12 +96,37 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
   unsigned char* b_hi = a_hi + kParts * op_bytes;
   unsigned char* b_lo = b_hi + op_bytes;
   float* staging = reinterpret_cast<float*>(b_hi + kParts * op_bytes);
-  float* bias = staging + kTcRows * feats;
+  float* bias = staging + kTcRows * feats + 8;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(bias + 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int c0 = blockIdx.y * 128;
+
+  const int n_tiles = ceil_div(m, nodes_per_tile);
+  const long long total_f = (long long)m * members * feats;
+  // floats between the 16-byte boundary below the tile's first element and that element
+  auto misalign = [&](int tile) -> int {
+    const float* first = ens + (size_t)tile * nodes_per_tile * members * feats;
+    return (int)((reinterpret_cast<uintptr_t>(first) & 15) >> 2);
+  };
+  auto prefetch = [&](int tile) {
+    const int n0 = tile * nodes_per_tile;
+    const int mis = misalign(tile);
+    const long long g0 = (long long)n0 * members * feats - mis;        // float index of the first chunk (may be < 0)
+    const int nch = (mis + min(nodes_per_tile, m - n0) * members * feats + 3) >> 2;
+    for (int c = tid; c < nch; c += kTcThreads) {
+      const long long g = g0 + 4 * c;
+      if (g >= 0 && g + 4 <= total_f) {
+        cp_async16(smem_u32(staging + 4 * c), ens + g);
+      } else {                                                           // the chunk straddles an end of the buffer
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (g + e >= 0 && g + e < total_f) staging[4 * c + e] = __ldg(ens + g + e);
+      }
+    }
+  };
+  if ((int)blockIdx.x < n_tiles) prefetch(blockIdx.x);
 
   // ---- one-time setup: TMEM (128 fp32 accumulator columns), mbarrier, W1 tile, bias
   if (warp == 0) {
@@ -112,8 +161,9 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
       }
     }
   }
+  cp_async_wait_all();
   asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
+  __syncthreads();                                        // the first tile has landed, the W1 tile is in place
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
   const float my_bias = bias[tid];
@@ -123,20 +173,36 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
   const int ksteps = chunks / 2;                         // one MMA covers 32 bytes of K = 2 chunks
   uint32_t phase = 0;
 
-  const int n_tiles = ceil_div(m, nodes_per_tile);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int n0 = tile * nodes_per_tile;
     const int n_nodes = min(nodes_per_tile, m - n0);
     const int rows = n_nodes * members;
-    // ---- stage the tile's member rows (contiguous in HBM): coalesced 4-byte loads
-    const float* src = ens + (size_t)n0 * members * feats;
-    const int total = rows * feats;
-    for (int idx = tid; idx < total; idx += kTcThreads) staging[idx] = __ldg(src + idx);
-    __syncthreads();
-    // ---- thread <-> member row: convert to the operand format and write the canonical K-major layout
+    // ---- thread <-> member row: convert the staged rows to the operand format, canonical K-major layout
     {
-      const float* row = staging + tid * feats;
+      const float* row = staging + misalign(tile) + tid * feats;
       const bool live = tid < rows;
+      if constexpr (KQ > 0) {
+        constexpr int KP = BF16 ? (8 * KQ + 15) / 16 * 16 : 8 * KQ;
+        constexpr int CH = KP / kElemsPerChunk;                       // == chunks (checked at launch)
+        float v[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v[k] = (live && k < feats) ? row[k] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (BF16) {
+            __nv_bfloat162 p[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(v[c * kElemsPerChunk + 2 * e], v[c * kElemsPerChunk + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(b_hi + c * kTcChunkBytes + tid * 16) = *reinterpret_cast<uint4*>(p);
+          } else {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(v[c * 4 + e]); lo[e] = v[c * 4 + e] - hi[e]; }
+            *reinterpret_cast<float4*>(b_hi + c * kTcChunkBytes + tid * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(b_lo + c * kTcChunkBytes + tid * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      } else
       for (int c = 0; c < chunks; ++c) {
         float v[8];
 #pragma unroll
@@ -160,7 +226,8 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    __syncthreads();                                                // B is complete, nobody reads the staged rows any more
+    if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     // ---- one thread issues the MMAs; completion arrives on the mbarrier
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
@@ -180,30 +247,40 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     mbar_wait(smem_u32(mbar), phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;");
-    // ---- epilogue: lane = channel; walk the 128 columns (member rows) 32 at a time, pool per station
-    {
-      const int col = c0 + tid;
+    // ---- epilogue: lane = channel, column = member row; pool per station (members summed in index order)
+    const int col = c0 + tid;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if constexpr (MEMBERS > 0) {
+      constexpr int NPT = kTcRows / MEMBERS;               // == nodes_per_tile (checked at launch)
+      constexpr int NQ = (NPT * MEMBERS + 31) / 32;
+      uint32_t r[NQ][32];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) tmem_ld32(taddr0 + (uint32_t)(q * 32), r[q]);
+      tmem_ld_wait();
+      float acc[NPT];
+#pragma unroll
+      for (int j = 0; j < NPT; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < NPT * MEMBERS; ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[c >> 5][c & 31]) + my_bias, 0.f);
+      if (col < hidden) {
+#pragma unroll
+        for (int j = 0; j < NPT; ++j)
+          if (j < n_nodes) pooled[(size_t)(n0 + j) * hidden + col] = acc[j];
+      }
+    } else {
       float sum = 0.f;
       int cnt = 0, node = n0;
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         if (q * 32 >= rows) break;
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32);
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_ld32(taddr0 + (uint32_t)(q * 32), r);
+        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (q * 32 + i < rows) {
             sum += fmaxf(__uint_as_float(r[i]) + my_bias, 0.f);
-            if (++cnt == members) {                      // members are pooled in index order
+            if (++cnt == members) {
               if (col < hidden) pooled[(size_t)node * hidden + col] = sum;
               sum = 0.f; cnt = 0; ++node;
             }
@@ -211,15 +288,16 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
         }
       }
     }
+    cp_async_wait_all();
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();                                      // TMEM, staging and the B tile are free again
+    __syncthreads();                                      // TMEM and the B tile are free again, the next tile has landed
   }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128));
 }
 
 static size_t tc_smem_bytes(bool bf16, int feats, int chunks) {
   const size_t op = (size_t)chunks * kTcChunkBytes;
-  return (bf16 ? 2 : 4) * op + (size_t)kTcRows * feats * sizeof(float) + 128 * sizeof(float) + 64;
+  return (bf16 ? 2 : 4) * op + ((size_t)kTcRows * feats + 8) * sizeof(float) + 128 * sizeof(float) + 64;
 }
 
 // Is the tensor-core path applicable (and worth it) for this shape?
@@ -235,6 +313,39 @@ bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden) {
   return (long long)num_nodes * members >= 65536 && hidden % 128 == 0;
 }
 
+template <bool BF16, int MEMBERS, int KQ>
+static int launch_tc_inst(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes, int members,
+                          int feats, int hidden, int npt, int chunks, dim3 grid, size_t smem, cudaStream_t s) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(deepsets_pool_fwd_tc_kernel<BF16, MEMBERS, KQ>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core path: %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  deepsets_pool_fwd_tc_kernel<BF16, MEMBERS, KQ><<<grid, kTcThreads, smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats,
+                                                                              hidden, npt, chunks);
+  return check_launch("deepsets_pool_fwd_tc_kernel");
+}
+
+template <bool BF16, int MEMBERS>
+static int launch_tc_members(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes, int members,
+                             int feats, int hidden, int npt, int chunks, dim3 grid, size_t smem, cudaStream_t s) {
+  if (ceil_div(feats, 8) == 5)           // 33..40 features (the reference has 35)
+    return launch_tc_inst<BF16, MEMBERS, 5>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+  return launch_tc_inst<BF16, MEMBERS, 0>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+}
+
+template <bool BF16>
+static int launch_tc(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes, int members, int feats,
+                     int hidden, int npt, int chunks, dim3 grid, size_t smem, cudaStream_t s) {
+  switch (members) {                     // the reference's ensembles: 11 reforecast members, 51 forecast members
+    case 11: return launch_tc_members<BF16, 11>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+    case 51: return launch_tc_members<BF16, 51>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+    default: return launch_tc_members<BF16, 0>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+  }
+}
+
 int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
                            int members, int feats, int hidden, cudaStream_t s) {
   const int kp = bf16 ? ((feats + 15) / 16) * 16 : ((feats + 7) / 8) * 8;
@@ -245,16 +356,8 @@ int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const f
   int gx = 2 * kNumSMs;
   if (gx > n_tiles) gx = n_tiles;
   dim3 grid(gx, ceil_div(hidden, 128));
-  static size_t attr[2] = {0, 0};
-  if (smem > attr[bf16]) {
-    cudaError_t e = bf16 ? cudaFuncSetAttribute(deepsets_pool_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(deepsets_pool_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core path: %s", cudaGetErrorString(e));
-    attr[bf16] = smem;
-  }
-  if (bf16) deepsets_pool_fwd_tc_kernel<true><<<grid, kTcThreads, smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks);
-  else deepsets_pool_fwd_tc_kernel<false><<<grid, kTcThreads, smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks);
-  return check_launch("deepsets_pool_fwd_tc_kernel");
+  return bf16 ? launch_tc<true>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s)
+              : launch_tc<false>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
 }
 
 }  // namespace rc

@@ -398,6 +398,27 @@ def test_deepsets_tensor_core_path_fp32(dev, m, em, f, h):
     assert rel_err(_np(out), want.numpy()) < TOL
 
 
+@pytest.mark.parametrize("m,em,f,h,shift", [(1301, 51, 35, 128, 1), (6001, 11, 35, 128, 3), (2201, 30, 33, 128, 2)])
+def test_deepsets_tensor_core_unaligned_ensemble(dev, m, em, f, h, shift):
+    """The member rows travel as 16-byte cp.async chunks of the aligned span around each tile: an ensemble that starts
+    1-3 floats past a 16-byte boundary (and ends as far before one) must give the same pooled sums."""
+    from raincast_gnn_b200 import _lib
+    g = torch.Generator().manual_seed(m + em)
+    ens = torch.randn(m, em, f, generator=g)
+    w1 = (torch.rand(h, f, generator=g) * 2 - 1) / f ** 0.5
+    b1 = torch.randn(h, generator=g) * 0.1
+    want = torch.relu(ens.double() @ w1.double().T + b1.double()).sum(1)
+    buf = torch.full((m * em * f + shift,), float("nan"), device=dev)       # NaN before the first element: must not be read in
+    buf[shift:] = ens.reshape(-1).to(dev)
+    ed = buf[shift:]
+    assert ed.data_ptr() % 16 == 4 * shift
+    wd, bd = w1.to(dev), b1.to(dev)
+    out = torch.empty(m, h, device=dev)
+    _lib.check(_lib.lib().rc_deepsets_pool_fwd(ed.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), m, em, f, h,
+                                               torch.cuda.current_stream().cuda_stream))
+    assert rel_err(_np(out), want.numpy()) < TOL
+
+
 @pytest.mark.parametrize("m,em,f,h", [(2000, 51, 35, 512), (977, 11, 35, 128), (64, 10, 35, 512), (300, 128, 64, 128)])
 def test_deepsets_tensor_core_path_bf16(dev, m, em, f, h):
     """BASELINE.json config 5: bf16 operands, fp32 accumulate / pool / output; 1e-2 against the float64 oracle."""
