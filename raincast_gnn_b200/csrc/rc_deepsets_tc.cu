@@ -21,7 +21,9 @@
 
 namespace rc {
 
-constexpr int kTcThreads = 128;
+// threads per member row / hidden channel (they split the K chunks and the accumulator columns): measured at config 4 / 5,
+// fp32 mode 470 us with one, 438 us with two; bf16 mode (H = 512) 908 us with one, 1145 us with two
+__host__ __device__ constexpr int tc_threads_per_row(bool bf16) { return bf16 ? 1 : 2; }
 constexpr int kTcRows = 128;          // MMA N: member rows per tile
 constexpr int kTcChunkBytes = kTcRows * 16;   // one 16-byte K chunk for 128 rows
 
@@ -75,7 +77,7 @@ __device__ __forceinline__ float to_tf32(float v) {
 }
 
 // dynamic shared memory (bytes), all 16-byte aligned:
-//   A_hi [chunks][128][16] | A_lo (fp32 mode) | B_hi | B_lo (fp32 mode) | staging [128*feats + 8] fp32 | bias [128] | mbar | tmem ptr
+//   A_hi [chunks][128][16] | A_lo (fp32 mode) | B_hi | B_lo (fp32 mode) | staging [128*feats + 8] fp32 | bias [128] | part [128] | mbar | tmem ptr
 // A tile's member rows are contiguous in HBM; they travel as 16-byte cp.async chunks of the aligned span that covers them
 // (the tile starts `mis` floats into the first chunk), issued for tile i+1 right after tile i has been converted, so the
 // HBM latency of the next tile hides behind the MMAs, the TMEM read-back and the pooling of the current one.
@@ -83,12 +85,14 @@ __device__ __forceinline__ float to_tf32(float v) {
 // 11 and 51 members and its 35 features): station boundaries in the pooling epilogue and the operand conversion are then
 // static - no per-column boundary test or branch, all shared-memory loads of a row in flight at once.  0 = any value.
 template <bool BF16, int MEMBERS, int KQ>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(128 * tc_threads_per_row(BF16))
 deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restrict__ w1, const float* __restrict__ b1,
                             float* __restrict__ pooled, int m, int members, int feats, int hidden, int nodes_per_tile,
                             int chunks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kParts = BF16 ? 1 : 2;                 // hi (+ lo)
+  constexpr int NH = tc_threads_per_row(BF16);
+  constexpr int kTcThreads = 128 * NH;
   constexpr int kElemsPerChunk = BF16 ? 8 : 4;
   const int op_bytes = chunks * kTcChunkBytes;
   unsigned char* a_hi = smem_raw;
@@ -97,10 +101,12 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
   unsigned char* b_lo = b_hi + op_bytes;
   float* staging = reinterpret_cast<float*>(b_hi + kParts * op_bytes);
   float* bias = staging + kTcRows * feats + 8;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(bias + 128);
+  float* part = bias + 128;                            // upper-half partial sum of the station that straddles column 64
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(part + 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int lane_row = tid & 127, half = tid >> 7;      // row of the operand tile / TMEM lane, and which half of its work
   const int c0 = blockIdx.y * 128;
 
   const int n_tiles = ceil_div(m, nodes_per_tile);
@@ -138,9 +144,9 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   {
-    const int col = c0 + tid;                            // thread <-> hidden channel (row of the A tile)
-    bias[tid] = col < hidden ? __ldg(b1 + col) : 0.f;
-    for (int c = 0; c < chunks; ++c) {
+    const int col = c0 + lane_row;                       // thread pair <-> hidden channel (row of the A tile)
+    if (half == 0) bias[lane_row] = col < hidden ? __ldg(b1 + col) : 0.f;
+    for (int c = half; c < chunks; c += NH) {
       float v[8];
 #pragma unroll
       for (int e = 0; e < kElemsPerChunk; ++e) {
@@ -151,13 +157,13 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
         __nv_bfloat162 p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-        *reinterpret_cast<uint4*>(a_hi + c * kTcChunkBytes + tid * 16) = *reinterpret_cast<uint4*>(p);
+        *reinterpret_cast<uint4*>(a_hi + c * kTcChunkBytes + lane_row * 16) = *reinterpret_cast<uint4*>(p);
       } else {
         float hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(v[e]); lo[e] = v[e] - hi[e]; }
-        *reinterpret_cast<float4*>(a_hi + c * kTcChunkBytes + tid * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(a_lo + c * kTcChunkBytes + tid * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(a_hi + c * kTcChunkBytes + lane_row * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a_lo + c * kTcChunkBytes + lane_row * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   }
@@ -166,7 +172,7 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
   __syncthreads();                                        // the first tile has landed, the W1 tile is in place
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
-  const float my_bias = bias[tid];
+  const float my_bias = bias[lane_row];
   // instruction descriptor: D fp32, A/B tf32 (2) or bf16 (1), both K-major, N = 128 (>>3), M = 128 (>>4)
   const uint32_t fmt = BF16 ? 1u : 2u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTcRows >> 3) << 17) | ((128u >> 4) << 24);
@@ -177,50 +183,44 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     const int n0 = tile * nodes_per_tile;
     const int n_nodes = min(nodes_per_tile, m - n0);
     const int rows = n_nodes * members;
-    // ---- thread <-> member row: convert the staged rows to the operand format, canonical K-major layout
+    // ---- thread pair <-> member row: convert the staged rows to the operand format, canonical K-major layout
     {
-      const float* row = staging + misalign(tile) + tid * feats;
-      const bool live = tid < rows;
-      if constexpr (KQ > 0) {
-        constexpr int KP = BF16 ? (8 * KQ + 15) / 16 * 16 : 8 * KQ;
-        constexpr int CH = KP / kElemsPerChunk;                       // == chunks (checked at launch)
-        float v[KP];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) v[k] = (live && k < feats) ? row[k] : 0.f;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          if (BF16) {
-            __nv_bfloat162 p[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(v[c * kElemsPerChunk + 2 * e], v[c * kElemsPerChunk + 2 * e + 1]);
-            *reinterpret_cast<uint4*>(b_hi + c * kTcChunkBytes + tid * 16) = *reinterpret_cast<uint4*>(p);
-          } else {
-            float hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(v[c * 4 + e]); lo[e] = v[c * 4 + e] - hi[e]; }
-            *reinterpret_cast<float4*>(b_hi + c * kTcChunkBytes + tid * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(b_lo + c * kTcChunkBytes + tid * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-      } else
-      for (int c = 0; c < chunks; ++c) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < kElemsPerChunk; ++e) {
-          const int k = c * kElemsPerChunk + e;
-          v[e] = (live && k < feats) ? row[k] : 0.f;
-        }
+      const float* row = staging + misalign(tile) + lane_row * feats;
+      const bool live = lane_row < rows;
+      auto put_chunk = [&](int c, const float* v) {                   // kElemsPerChunk values -> 16 bytes of B_hi (and B_lo)
         if (BF16) {
           __nv_bfloat162 p[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) p[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          *reinterpret_cast<uint4*>(b_hi + c * kTcChunkBytes + tid * 16) = *reinterpret_cast<uint4*>(p);
+          *reinterpret_cast<uint4*>(b_hi + c * kTcChunkBytes + lane_row * 16) = *reinterpret_cast<uint4*>(p);
         } else {
           float hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { hi[e] = to_tf32(v[e]); lo[e] = v[e] - hi[e]; }
-          *reinterpret_cast<float4*>(b_hi + c * kTcChunkBytes + tid * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(b_lo + c * kTcChunkBytes + tid * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<float4*>(b_hi + c * kTcChunkBytes + lane_row * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(b_lo + c * kTcChunkBytes + lane_row * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      };
+      if constexpr (KQ > 0) {
+        constexpr int KP = BF16 ? (8 * KQ + 15) / 16 * 16 : 8 * KQ;
+        constexpr int CH = KP / kElemsPerChunk;                       // == chunks (checked at launch)
+        static_assert(CH % NH == 0, "the threads of a row take the same number of chunks each");
+        constexpr int HC = CH / NH, HK = HC * kElemsPerChunk;
+        const int k0 = half * HK;
+        float v[HK];
+#pragma unroll
+        for (int k = 0; k < HK; ++k) v[k] = (live && k0 + k < feats) ? row[k0 + k] : 0.f;
+#pragma unroll
+        for (int cc = 0; cc < HC; ++cc) put_chunk(half * HC + cc, v + cc * kElemsPerChunk);
+      } else {
+        for (int c = half; c < chunks; c += NH) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < kElemsPerChunk; ++e) {
+            const int k = c * kElemsPerChunk + e;
+            v[e] = (live && k < feats) ? row[k] : 0.f;
+          }
+          put_chunk(c, v);
         }
       }
     }
@@ -248,26 +248,45 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;");
     // ---- epilogue: lane = channel, column = member row; pool per station (members summed in index order)
-    const int col = c0 + tid;
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int col = c0 + lane_row;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     if constexpr (MEMBERS > 0) {
+      // thread `half` of a channel takes columns [W*half, W*half + W); with two threads the station that straddles column 64
+      // is finished by the lower one from the upper one's partial sum
       constexpr int NPT = kTcRows / MEMBERS;               // == nodes_per_tile (checked at launch)
-      constexpr int NQ = (NPT * MEMBERS + 31) / 32;
-      uint32_t r[NQ][32];
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) tmem_ld32(taddr0 + (uint32_t)(q * 32), r[q]);
-      tmem_ld_wait();
+      constexpr int USED = NPT * MEMBERS;
+      constexpr int W = kTcRows / NH, NQ = W / 32;
+      constexpr int JS = 63 / MEMBERS;                     // station that owns column 63
+      constexpr bool STRADDLE = NH == 2 && (JS + 1) * MEMBERS > 64 && USED > 64;
       float acc[NPT];
 #pragma unroll
       for (int j = 0; j < NPT; ++j) acc[j] = 0.f;
+      uint32_t r[NQ][32];
 #pragma unroll
-      for (int c = 0; c < NPT * MEMBERS; ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[c >> 5][c & 31]) + my_bias, 0.f);
+      for (int q = 0; q < NQ; ++q)
+        if (W * half + 32 * q < USED) tmem_ld32(taddr0 + (uint32_t)(W * half + 32 * q), r[q]);
+      tmem_ld_wait();
+      if (half == 0) {
+#pragma unroll
+        for (int c = 0; c < (USED < W ? USED : W); ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[c >> 5][c & 31]) + my_bias, 0.f);
+      } else {
+#pragma unroll
+        for (int c = W; c < USED; ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[(c - W) >> 5][c & 31]) + my_bias, 0.f);
+        if (STRADDLE) part[lane_row] = acc[JS];
+      }
+      if (STRADDLE) __syncthreads();
       if (col < hidden) {
 #pragma unroll
-        for (int j = 0; j < NPT; ++j)
-          if (j < n_nodes) pooled[(size_t)(n0 + j) * hidden + col] = acc[j];
+        for (int j = 0; j < NPT; ++j) {
+          const bool lower = NH == 1 || (j + 1) * MEMBERS <= 64 || (STRADDLE && j == JS);     // who writes station j
+          if (j < n_nodes && (half == 0) == lower) {
+            float v = acc[j];
+            if (STRADDLE && j == JS) v += part[lane_row];
+            pooled[(size_t)(n0 + j) * hidden + col] = v;
+          }
+        }
       }
-    } else {
+    } else if (half == 0) {
       float sum = 0.f;
       int cnt = 0, node = n0;
 #pragma unroll 1
@@ -297,7 +316,7 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
 
 static size_t tc_smem_bytes(bool bf16, int feats, int chunks) {
   const size_t op = (size_t)chunks * kTcChunkBytes;
-  return (bf16 ? 2 : 4) * op + ((size_t)kTcRows * feats + 8) * sizeof(float) + 128 * sizeof(float) + 64;
+  return (bf16 ? 2 : 4) * op + ((size_t)kTcRows * feats + 8) * sizeof(float) + 256 * sizeof(float) + 64;
 }
 
 // Is the tensor-core path applicable (and worth it) for this shape?
@@ -323,7 +342,7 @@ static int launch_tc_inst(const float* ens, const float* w1, const float* b1, fl
     if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core path: %s", cudaGetErrorString(e));
     attr = smem;
   }
-  deepsets_pool_fwd_tc_kernel<BF16, MEMBERS, KQ><<<grid, kTcThreads, smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats,
+  deepsets_pool_fwd_tc_kernel<BF16, MEMBERS, KQ><<<grid, 128 * tc_threads_per_row(BF16), smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats,
                                                                               hidden, npt, chunks);
   return check_launch("deepsets_pool_fwd_tc_kernel");
 }
