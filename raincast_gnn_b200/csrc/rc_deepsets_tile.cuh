@@ -185,8 +185,11 @@ __device__ __forceinline__ void ds_fwd_tile(const DsFwdP& p, const uint3 bid, co
 // Tiles of 64 consecutive member rows of the flattened [M*members, F] matrix.
 //   phase 1: recompute pre = E W1^T + b1 for the tile (warp owns 8 rows, lane 4 columns), and write
 //            dh[r][c] = d_pooled[node(r)][c] * 1[pre > 0] to shared memory;
-//   phase 2: thread (c = tid % 128, half = tid / 128) accumulates d w1[c][k] over the tile's rows for
-//            its 4*KQ features in registers; the accumulators live across all tiles of the CTA.
+//   phase 2: thread (cp = tid % 64, fh = tid / 64 % 2, rh = tid / 128) accumulates d w1[c][k] for its two columns
+//            2cp, 2cp+1 and its 4*KQ features over its half of the tile's rows (32 * rh ...) in registers; the accumulators
+//            live across all tiles of the CTA and the two row halves are added through shared memory at the end.
+//            (At scale the kernel is bound by the shared-memory pipe - ncu: l1tex 73 %, FMA pipe 46 % - and two columns per
+//            thread read every broadcast feature value once per two columns: 7 wavefronts per 40 FFMA instead of 12.)
 // dynamic smem: Ws[FP][128] | bias[128] | Es[64][FP] | dh[64][128],  FP = 8*KQ >= feats
 template <int KQ>
 __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, const uint3 gdim, float* smem) {
@@ -214,12 +217,12 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
   for (int j = tid; j < kDsCols; j += kDsThreads) bias[j] = c0 + j < hidden ? __ldg(b1 + c0 + j) : 0.f;
   const float4 bv_dummy = make_float4(0.f, 0.f, 0.f, 0.f);
   (void)bv_dummy;
-  float dwacc[4 * KQ];
+  float dwacc[2][4 * KQ];
 #pragma unroll
-  for (int i = 0; i < 4 * KQ; ++i) dwacc[i] = 0.f;
-  float dbacc = 0.f;
+  for (int i = 0; i < 4 * KQ; ++i) dwacc[0][i] = dwacc[1][i] = 0.f;
+  float dbacc[2] = {0.f, 0.f};
   const long long total_rows = (long long)m * members;
-  const int c_own = tid & (kDsCols - 1), half = tid >> 7;
+  const int cp = tid & 63, fh = (tid >> 6) & 1, rh = tid >> 7;
   __syncthreads();
   const float4 bv = ld4(bias + 4 * lane);
   for (long long row0 = (long long)bid.x * ROWS; row0 < total_rows; row0 += (long long)gdim.x * ROWS) {
@@ -289,31 +292,54 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
     }
     __syncthreads();
     // phase 2
+    {
+      const int r_end = min(nrows, 32 * rh + 32);
 #pragma unroll 4
-    for (int r = 0; r < nrows; ++r) {
-      const float d = dh[r * kDsCols + c_own];
-      if (half == 0) dbacc += d;
+      for (int r = 32 * rh; r < r_end; ++r) {
+        const float2 d = *reinterpret_cast<const float2*>(dh + r * kDsCols + 2 * cp);
+        if (fh == 0) { dbacc[0] += d.x; dbacc[1] += d.y; }
 #pragma unroll
-      for (int q = 0; q < KQ; ++q) {
-        const float4 e = ld4(Es + r * FP + half * 4 * KQ + 4 * q);
-        dwacc[4 * q + 0] = fmaf(d, e.x, dwacc[4 * q + 0]);
-        dwacc[4 * q + 1] = fmaf(d, e.y, dwacc[4 * q + 1]);
-        dwacc[4 * q + 2] = fmaf(d, e.z, dwacc[4 * q + 2]);
-        dwacc[4 * q + 3] = fmaf(d, e.w, dwacc[4 * q + 3]);
+        for (int q = 0; q < KQ; ++q) {
+          const float4 e = ld4(Es + r * FP + fh * 4 * KQ + 4 * q);
+          dwacc[0][4 * q + 0] = fmaf(d.x, e.x, dwacc[0][4 * q + 0]); dwacc[1][4 * q + 0] = fmaf(d.y, e.x, dwacc[1][4 * q + 0]);
+          dwacc[0][4 * q + 1] = fmaf(d.x, e.y, dwacc[0][4 * q + 1]); dwacc[1][4 * q + 1] = fmaf(d.y, e.y, dwacc[1][4 * q + 1]);
+          dwacc[0][4 * q + 2] = fmaf(d.x, e.z, dwacc[0][4 * q + 2]); dwacc[1][4 * q + 2] = fmaf(d.y, e.z, dwacc[1][4 * q + 2]);
+          dwacc[0][4 * q + 3] = fmaf(d.x, e.w, dwacc[0][4 * q + 3]); dwacc[1][4 * q + 3] = fmaf(d.y, e.w, dwacc[1][4 * q + 3]);
+        }
       }
     }
     __syncthreads();
   }
+  // the upper row half hands its sums to the lower one through shared memory (Es | dh are free and contiguous:
+  // [8*KQ + 2][128] floats <= [64][8*KQ + 128])
+  {
+    float* comb = Es + (tid & 127);
+    if (rh == 1) {
+#pragma unroll
+      for (int i = 0; i < 4 * KQ; ++i) { comb[(2 * i) * 128] = dwacc[0][i]; comb[(2 * i + 1) * 128] = dwacc[1][i]; }
+      comb[(8 * KQ) * 128] = dbacc[0];
+      comb[(8 * KQ + 1) * 128] = dbacc[1];
+    }
+    __syncthreads();
+    if (rh == 1) return;
+#pragma unroll
+    for (int i = 0; i < 4 * KQ; ++i) { dwacc[0][i] += comb[(2 * i) * 128]; dwacc[1][i] += comb[(2 * i + 1) * 128]; }
+    dbacc[0] += comb[(8 * KQ) * 128];
+    dbacc[1] += comb[(8 * KQ + 1) * 128];
+  }
   // partials[bid.x][hidden*feats + hidden]: every CTA of column chunk bid.y writes its slice
   float* out = partials + (size_t)bid.x * ((size_t)hidden * feats + hidden);
-  const int col = c0 + c_own;
-  if (col < hidden) {
 #pragma unroll
-    for (int i = 0; i < 4 * KQ; ++i) {
-      const int k = half * 4 * KQ + i;
-      if (k < feats) out[(size_t)col * feats + k] = dwacc[i];
+  for (int j = 0; j < 2; ++j) {
+    const int col = c0 + 2 * cp + j;
+    if (col < hidden) {
+#pragma unroll
+      for (int i = 0; i < 4 * KQ; ++i) {
+        const int k = fh * 4 * KQ + i;
+        if (k < feats) out[(size_t)col * feats + k] = dwacc[j][i];
+      }
+      if (fh == 0) out[(size_t)hidden * feats + col] = dbacc[j];
     }
-    if (half == 0) out[(size_t)hidden * feats + col] = dbacc;
   }
 }
 

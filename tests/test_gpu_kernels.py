@@ -234,7 +234,8 @@ def test_gine_aggregation_fwd_bwd(dev, golden_graph, name, batch, h):
 
 
 # ------------------------------------------------------------------------------------------------ DeepSets
-@pytest.mark.parametrize("m,em,f,h", [(976, 11, 35, 128), (30, 4, 7, 32), (100, 51, 35, 128), (64, 10, 35, 256), (17, 3, 5, 32)])
+@pytest.mark.parametrize("m,em,f,h", [(976, 11, 35, 128), (30, 4, 7, 32), (100, 51, 35, 128), (64, 10, 35, 256), (17, 3, 5, 32),
+                                       (50, 6, 64, 128), (333, 7, 20, 200)])
 def test_deepsets_block(dev, m, em, f, h):
     from oracle.model import DeepSetEncoder
     from raincast_gnn_b200 import kernels as K
