@@ -16,6 +16,8 @@ fp32): forward, CRPS, backward, gradient all-reduce (N > 1), AdamW.  Prints ONE 
            H=128): algorithmic bytes 2*M*H*4 + E*8 + (M+1)*4 + 8*H  (SURVEY.md 8d) / mean CUDA-event time;
            `bwd` and `batched_reference_graphs` (4096 reference graphs in one batch) report the same for the
            backward kernel and for the graph shape where HBM, not the SM, is the relevant bound
+           `deepsets_contraction`: the tcgen05 member contraction at the config-4 / config-5 shapes (TFLOP/s issued
+           against the measured dense peak, ensemble read rate against the HBM peak)
   cpu_baseline — the CPU oracle (reference modules' arithmetic, oracle/) timed on this box's host cores
 """
 from __future__ import annotations
@@ -229,6 +231,44 @@ def measure_aggregation(dev, iters: int = 20, which: str = "config4"):
     return res, bytes_fwd, bytes_bwd, n, e
 
 
+def measure_deepsets_contraction(dev, peaks, iters: int = 5):
+    """The tcgen05 member contraction (Linear + ReLU + sum over members) at the config-4 shape (fp32-accurate 3xTF32) and
+    the config-5 shape (bf16 operands, H = 512): CUDA-event time per launch, algorithmic TFLOP/s (2*M*Em*F*H), the tensor
+    work actually issued against the measured dense peak (TF32 = half the bf16 rate, three products per fp32 product,
+    K padded to the MMA's k-block), and the ensemble read rate against the HBM peak."""
+    from raincast_gnn_b200 import _lib
+    L = _lib.lib()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    m, em, f = 100_000, 51, FEATS
+    g = torch.Generator().manual_seed(0)
+    ens = torch.randn(m, em, f, generator=g).to(dev)
+    out = {}
+    for tag, h, bf16 in (("config4_fp32_3xtf32", HIDDEN, False), ("config5_bf16_h512", 512, True)):
+        w1 = (torch.randn(h, f, generator=g) * 0.2).to(dev)
+        b1 = torch.randn(h, generator=g).to(dev)
+        pooled = torch.empty(m, h, device=dev)
+        fn = L.rc_deepsets_pool_fwd_bf16 if bf16 else L.rc_deepsets_pool_fwd
+        run = lambda: _lib.check(fn(ens.data_ptr(), w1.data_ptr(), b1.data_ptr(), pooled.data_ptr(), m, em, f, h, st))
+        for _ in range(2):
+            run()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            run()
+        c.record()
+        c.synchronize()
+        ms = a.elapsed_time(c) / iters                      # the 714 MB ensemble is larger than L2: every launch reads HBM
+        kpad = (f + 15) // 16 * 16 if bf16 else (f + 7) // 8 * 8
+        issued = 2.0 * (m * em) * kpad * h * (1 if bf16 else 3)
+        peak_tf = peaks.get("bf16_tflops", 1686.5) * (1.0 if bf16 else 0.5)
+        out[tag] = {"workload": f"{m} stations x {em} members x {f} features -> H={h}", "us_per_launch": ms * 1e3,
+                    "tflops_algorithmic": 2.0 * m * em * f * h / ms / 1e9, "tflops_issued": issued / ms / 1e9,
+                    "tensor_peak_tflops": peak_tf, "frac_tensor": issued / ms / 1e9 / peak_tf,
+                    "ens_read_gbs": ens.numel() * 4 / ms / 1e6, "frac_hbm": ens.numel() * 4 / ms / 1e6 / peaks["hbm_gbs"]}
+        del w1, b1, pooled
+    return out
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -343,6 +383,10 @@ def run_b200(args):
                         "us_per_launch": res2["fwd"] * 1e3, "algorithmic_bytes": bf2},
                 "bwd": {"achieved": bb2 / (res2["bwd"] * 1e-3) / 1e9, "frac": bb2 / (res2["bwd"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                         "us_per_launch": res2["bwd"] * 1e3, "algorithmic_bytes": bb2}}
+            try:        # second north-star kernel: the DeepSets member contraction on tcgen05 (reported, not the headline)
+                line["roofline"]["deepsets_contraction"] = measure_deepsets_contraction(dev, peaks)
+            except Exception as exc:        # never lose the bench line over the extra leg
+                line["roofline"]["deepsets_contraction"] = {"error": repr(exc)}
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     tr = json.load(f)
