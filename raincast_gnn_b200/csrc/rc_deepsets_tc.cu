@@ -77,7 +77,10 @@ __device__ __forceinline__ float to_tf32(float v) {
 }
 
 // dynamic shared memory (bytes), all 16-byte aligned:
-//   A_hi [chunks][128][16] | A_lo (fp32 mode) | B_hi | B_lo (fp32 mode) | staging [128*feats + 8] fp32 | bias [128] | part [128] | mbar | tmem ptr
+//   ny x { A_hi [chunks][128][16] | A_lo (fp32 mode) } | B_hi | B_lo (fp32 mode) | staging [128*feats + 8] fp32 | bias [ny*128] | part [128] | mbar | tmem ptr
+// ny = hidden-channel chunks (of 128) handled inside one CTA: a tile's member rows are staged and converted once and
+// multiplied with ny W1 tiles one after the other (bf16 mode, where ny W1 tiles fit beside two CTAs per SM); with ny = 1 the
+// chunks are blockIdx.y.
 // A tile's member rows are contiguous in HBM; they travel as 16-byte cp.async chunks of the aligned span that covers them
 // (the tile starts `mis` floats into the first chunk), issued for tile i+1 right after tile i has been converted, so the
 // HBM latency of the next tile hides behind the MMAs, the TMEM read-back and the pooling of the current one.
@@ -88,26 +91,25 @@ template <bool BF16, int MEMBERS, int KQ>
 __global__ void __launch_bounds__(128 * tc_threads_per_row(BF16))
 deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restrict__ w1, const float* __restrict__ b1,
                             float* __restrict__ pooled, int m, int members, int feats, int hidden, int nodes_per_tile,
-                            int chunks) {
+                            int chunks, int ny) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kParts = BF16 ? 1 : 2;                 // hi (+ lo)
   constexpr int NH = tc_threads_per_row(BF16);
   constexpr int kTcThreads = 128 * NH;
   constexpr int kElemsPerChunk = BF16 ? 8 : 4;
   const int op_bytes = chunks * kTcChunkBytes;
-  unsigned char* a_hi = smem_raw;
-  unsigned char* a_lo = a_hi + op_bytes;
-  unsigned char* b_hi = a_hi + kParts * op_bytes;
+  const int a_bytes = kParts * op_bytes;               // one W1 tile: hi (+ lo)
+  unsigned char* b_hi = smem_raw + ny * a_bytes;
   unsigned char* b_lo = b_hi + op_bytes;
   float* staging = reinterpret_cast<float*>(b_hi + kParts * op_bytes);
   float* bias = staging + kTcRows * feats + 8;
-  float* part = bias + 128;                            // upper-half partial sum of the station that straddles column 64
+  float* part = bias + ny * 128;                           // upper-half partial sum of the station that straddles column 64
   uint64_t* mbar = reinterpret_cast<uint64_t*>(part + 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int lane_row = tid & 127, half = tid >> 7;      // row of the operand tile / TMEM lane, and which half of its work
-  const int c0 = blockIdx.y * 128;
+  const int c0 = blockIdx.y * 128 * ny;
 
   const int n_tiles = ceil_div(m, nodes_per_tile);
   const long long total_f = (long long)m * members * feats;
@@ -143,9 +145,11 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
-  {
-    const int col = c0 + lane_row;                       // thread pair <-> hidden channel (row of the A tile)
-    if (half == 0) bias[lane_row] = col < hidden ? __ldg(b1 + col) : 0.f;
+  for (int y = 0; y < ny; ++y) {
+    const int col = c0 + y * 128 + lane_row;             // thread pair <-> hidden channel (row of the A tile)
+    unsigned char* a_hi = smem_raw + y * a_bytes;
+    unsigned char* a_lo = a_hi + op_bytes;
+    if (half == 0) bias[y * 128 + lane_row] = col < hidden ? __ldg(b1 + col) : 0.f;
     for (int c = half; c < chunks; c += NH) {
       float v[8];
 #pragma unroll
@@ -172,7 +176,6 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
   __syncthreads();                                        // the first tile has landed, the W1 tile is in place
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
-  const float my_bias = bias[lane_row];
   // instruction descriptor: D fp32, A/B tf32 (2) or bf16 (1), both K-major, N = 128 (>>3), M = 128 (>>4)
   const uint32_t fmt = BF16 ? 1u : 2u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTcRows >> 3) << 17) | ((128u >> 4) << 24);
@@ -228,10 +231,11 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();                                                // B is complete, nobody reads the staged rows any more
     if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
-    // ---- one thread issues the MMAs; completion arrives on the mbarrier
+    for (int y = 0; y < ny; ++y) {
+    // ---- one thread issues the MMAs of this hidden chunk; completion arrives on the mbarrier
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      const uint32_t ah = smem_u32(smem_raw) + y * a_bytes, al = ah + op_bytes, bh = smem_u32(b_hi), bl = smem_u32(b_lo);
       for (int ks = 0; ks < ksteps; ++ks) {
         const uint32_t off = ks * 2 * kTcChunkBytes;
         if (BF16) {
@@ -248,7 +252,8 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;");
     // ---- epilogue: lane = channel, column = member row; pool per station (members summed in index order)
-    const int col = c0 + lane_row;
+    const int col = c0 + y * 128 + lane_row;
+    const float my_bias = bias[y * 128 + lane_row];
     const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     if constexpr (MEMBERS > 0) {
       // thread `half` of a channel takes columns [W*half, W*half + W); with two threads the station that straddles column 64
@@ -307,6 +312,11 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
         }
       }
     }
+    if (y + 1 < ny) {
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();                                    // the accumulator is free for the next chunk's MMAs
+    }
+    }  // hidden chunks
     cp_async_wait_all();
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();                                      // TMEM and the B tile are free again, the next tile has landed
@@ -314,9 +324,9 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128));
 }
 
-static size_t tc_smem_bytes(bool bf16, int feats, int chunks) {
+static size_t tc_smem_bytes(bool bf16, int feats, int chunks, int ny) {
   const size_t op = (size_t)chunks * kTcChunkBytes;
-  return (bf16 ? 2 : 4) * op + ((size_t)kTcRows * feats + 8) * sizeof(float) + 256 * sizeof(float) + 64;
+  return (bf16 ? 1 : 2) * op * (ny + 1) + ((size_t)kTcRows * feats + 8) * sizeof(float) + (ny + 1) * 128 * sizeof(float) + 64;
 }
 
 // Is the tensor-core path applicable (and worth it) for this shape?
@@ -334,7 +344,7 @@ bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden) {
 
 template <bool BF16, int MEMBERS, int KQ>
 static int launch_tc_inst(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes, int members,
-                          int feats, int hidden, int npt, int chunks, dim3 grid, size_t smem, cudaStream_t s) {
+                          int feats, int hidden, int npt, int chunks, int ny, dim3 grid, size_t smem, cudaStream_t s) {
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(deepsets_pool_fwd_tc_kernel<BF16, MEMBERS, KQ>,
@@ -343,25 +353,25 @@ static int launch_tc_inst(const float* ens, const float* w1, const float* b1, fl
     attr = smem;
   }
   deepsets_pool_fwd_tc_kernel<BF16, MEMBERS, KQ><<<grid, 128 * tc_threads_per_row(BF16), smem, s>>>(ens, w1, b1, pooled, num_nodes, members, feats,
-                                                                              hidden, npt, chunks);
+                                                                              hidden, npt, chunks, ny);
   return check_launch("deepsets_pool_fwd_tc_kernel");
 }
 
 template <bool BF16, int MEMBERS>
 static int launch_tc_members(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes, int members,
-                             int feats, int hidden, int npt, int chunks, dim3 grid, size_t smem, cudaStream_t s) {
+                             int feats, int hidden, int npt, int chunks, int ny, dim3 grid, size_t smem, cudaStream_t s) {
   if (ceil_div(feats, 8) == 5)           // 33..40 features (the reference has 35)
-    return launch_tc_inst<BF16, MEMBERS, 5>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
-  return launch_tc_inst<BF16, MEMBERS, 0>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+    return launch_tc_inst<BF16, MEMBERS, 5>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s);
+  return launch_tc_inst<BF16, MEMBERS, 0>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s);
 }
 
 template <bool BF16>
 static int launch_tc(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes, int members, int feats,
-                     int hidden, int npt, int chunks, dim3 grid, size_t smem, cudaStream_t s) {
+                     int hidden, int npt, int chunks, int ny, dim3 grid, size_t smem, cudaStream_t s) {
   switch (members) {                     // the reference's ensembles: 11 reforecast members, 51 forecast members
-    case 11: return launch_tc_members<BF16, 11>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
-    case 51: return launch_tc_members<BF16, 51>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
-    default: return launch_tc_members<BF16, 0>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+    case 11: return launch_tc_members<BF16, 11>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s);
+    case 51: return launch_tc_members<BF16, 51>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s);
+    default: return launch_tc_members<BF16, 0>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s);
   }
 }
 
@@ -369,14 +379,17 @@ int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const f
                            int members, int feats, int hidden, cudaStream_t s) {
   const int kp = bf16 ? ((feats + 15) / 16) * 16 : ((feats + 7) / 8) * 8;
   const int chunks = bf16 ? kp / 8 : kp / 4;
-  const size_t smem = tc_smem_bytes(bf16, feats, chunks);
+  // hidden chunks inside the CTA (member rows converted once per tile) where all the W1 tiles fit beside two CTAs per SM
+  const int hchunks = ceil_div(hidden, 128);
+  const int ny = (bf16 && tc_smem_bytes(bf16, feats, chunks, hchunks) <= 110 * 1024) ? hchunks : 1;
+  const size_t smem = tc_smem_bytes(bf16, feats, chunks, ny);
   const int npt = kTcRows / members;
   const int n_tiles = ceil_div(num_nodes, npt);
   int gx = 2 * kNumSMs;
   if (gx > n_tiles) gx = n_tiles;
-  dim3 grid(gx, ceil_div(hidden, 128));
-  return bf16 ? launch_tc<true>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s)
-              : launch_tc<false>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, grid, smem, s);
+  dim3 grid(gx, ceil_div(hchunks, ny));
+  return bf16 ? launch_tc<true>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s)
+              : launch_tc<false>(ens, w1, b1, pooled, num_nodes, members, feats, hidden, npt, chunks, ny, grid, smem, s);
 }
 
 }  // namespace rc
