@@ -232,90 +232,90 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     __syncthreads();                                                // B is complete, nobody reads the staged rows any more
     if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     for (int y = 0; y < ny; ++y) {
-    // ---- one thread issues the MMAs of this hidden chunk; completion arrives on the mbarrier
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint32_t ah = smem_u32(smem_raw) + y * a_bytes, al = ah + op_bytes, bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint32_t off = ks * 2 * kTcChunkBytes;
-        if (BF16) {
-          umma_bf16(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
-        } else {
-          umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
-          umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bl + off), idesc, 1);
-          umma_tf32(tmem_base, umma_desc(al + off), umma_desc(bh + off), idesc, 1);
-        }
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
-    }
-    mbar_wait(smem_u32(mbar), phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    // ---- epilogue: lane = channel, column = member row; pool per station (members summed in index order)
-    const int col = c0 + y * 128 + lane_row;
-    const float my_bias = bias[y * 128 + lane_row];
-    const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    if constexpr (MEMBERS > 0) {
-      // thread `half` of a channel takes columns [W*half, W*half + W); with two threads the station that straddles column 64
-      // is finished by the lower one from the upper one's partial sum
-      constexpr int NPT = kTcRows / MEMBERS;               // == nodes_per_tile (checked at launch)
-      constexpr int USED = NPT * MEMBERS;
-      constexpr int W = kTcRows / NH, NQ = W / 32;
-      constexpr int JS = 63 / MEMBERS;                     // station that owns column 63
-      constexpr bool STRADDLE = NH == 2 && (JS + 1) * MEMBERS > 64 && USED > 64;
-      float acc[NPT];
-#pragma unroll
-      for (int j = 0; j < NPT; ++j) acc[j] = 0.f;
-      uint32_t r[NQ][32];
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        if (W * half + 32 * q < USED) tmem_ld32(taddr0 + (uint32_t)(W * half + 32 * q), r[q]);
-      tmem_ld_wait();
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < (USED < W ? USED : W); ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[c >> 5][c & 31]) + my_bias, 0.f);
-      } else {
-#pragma unroll
-        for (int c = W; c < USED; ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[(c - W) >> 5][c & 31]) + my_bias, 0.f);
-        if (STRADDLE) part[lane_row] = acc[JS];
-      }
-      if (STRADDLE) __syncthreads();
-      if (col < hidden) {
-#pragma unroll
-        for (int j = 0; j < NPT; ++j) {
-          const bool lower = NH == 1 || (j + 1) * MEMBERS <= 64 || (STRADDLE && j == JS);     // who writes station j
-          if (j < n_nodes && (half == 0) == lower) {
-            float v = acc[j];
-            if (STRADDLE && j == JS) v += part[lane_row];
-            pooled[(size_t)(n0 + j) * hidden + col] = v;
+      // ---- one thread issues the MMAs of this hidden chunk; completion arrives on the mbarrier
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t ah = smem_u32(smem_raw) + y * a_bytes, al = ah + op_bytes, bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = ks * 2 * kTcChunkBytes;
+          if (BF16) {
+            umma_bf16(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
+          } else {
+            umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
+            umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bl + off), idesc, 1);
+            umma_tf32(tmem_base, umma_desc(al + off), umma_desc(bh + off), idesc, 1);
           }
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
       }
-    } else if (half == 0) {
-      float sum = 0.f;
-      int cnt = 0, node = n0;
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        if (q * 32 >= rows) break;
-        uint32_t r[32];
-        tmem_ld32(taddr0 + (uint32_t)(q * 32), r);
-        tmem_ld_wait();
+      mbar_wait(smem_u32(mbar), phase);
+      phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      // ---- epilogue: lane = channel, column = member row; pool per station (members summed in index order)
+      const int col = c0 + y * 128 + lane_row;
+      const float my_bias = bias[y * 128 + lane_row];
+      const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      if constexpr (MEMBERS > 0) {
+        // thread `half` of a channel takes columns [W*half, W*half + W); with two threads the station that straddles column 64
+        // is finished by the lower one from the upper one's partial sum
+        constexpr int NPT = kTcRows / MEMBERS;               // == nodes_per_tile (checked at launch)
+        constexpr int USED = NPT * MEMBERS;
+        constexpr int W = kTcRows / NH, NQ = W / 32;
+        constexpr int JS = 63 / MEMBERS;                     // station that owns column 63
+        constexpr bool STRADDLE = NH == 2 && (JS + 1) * MEMBERS > 64 && USED > 64;
+        float acc[NPT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (q * 32 + i < rows) {
-            sum += fmaxf(__uint_as_float(r[i]) + my_bias, 0.f);
-            if (++cnt == members) {
-              if (col < hidden) pooled[(size_t)node * hidden + col] = sum;
-              sum = 0.f; cnt = 0; ++node;
+        for (int j = 0; j < NPT; ++j) acc[j] = 0.f;
+        uint32_t r[NQ][32];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          if (W * half + 32 * q < USED) tmem_ld32(taddr0 + (uint32_t)(W * half + 32 * q), r[q]);
+        tmem_ld_wait();
+        if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < (USED < W ? USED : W); ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[c >> 5][c & 31]) + my_bias, 0.f);
+        } else {
+#pragma unroll
+          for (int c = W; c < USED; ++c) acc[c / MEMBERS] += fmaxf(__uint_as_float(r[(c - W) >> 5][c & 31]) + my_bias, 0.f);
+          if (STRADDLE) part[lane_row] = acc[JS];
+        }
+        if (STRADDLE) __syncthreads();
+        if (col < hidden) {
+#pragma unroll
+          for (int j = 0; j < NPT; ++j) {
+            const bool lower = NH == 1 || (j + 1) * MEMBERS <= 64 || (STRADDLE && j == JS);     // who writes station j
+            if (j < n_nodes && (half == 0) == lower) {
+              float v = acc[j];
+              if (STRADDLE && j == JS) v += part[lane_row];
+              pooled[(size_t)(n0 + j) * hidden + col] = v;
+            }
+          }
+        }
+      } else if (half == 0) {
+        float sum = 0.f;
+        int cnt = 0, node = n0;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          if (q * 32 >= rows) break;
+          uint32_t r[32];
+          tmem_ld32(taddr0 + (uint32_t)(q * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (q * 32 + i < rows) {
+              sum += fmaxf(__uint_as_float(r[i]) + my_bias, 0.f);
+              if (++cnt == members) {
+                if (col < hidden) pooled[(size_t)node * hidden + col] = sum;
+                sum = 0.f; cnt = 0; ++node;
+              }
             }
           }
         }
       }
-    }
-    if (y + 1 < ny) {
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      __syncthreads();                                    // the accumulator is free for the next chunk's MMAs
-    }
+      if (y + 1 < ny) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();                                    // the accumulator is free for the next chunk's MMAs
+      }
     }  // hidden chunks
     cp_async_wait_all();
     asm volatile("tcgen05.fence::before_thread_sync;");
