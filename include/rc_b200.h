@@ -316,26 +316,6 @@ int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, f
                       int64_t* step, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                       void* stream);
 
-/* ------------------------------------------------------------------------------------------------
- * Step program: record a sequence of the calls above and run it as ONE persistent cooperative kernel
- * (replaces the ~75 launches of a train.py iteration, train.py:61-71, at shapes where launch latency dominates)
- * ---------------------------------------------------------------------------------------------- */
-/* Between rc_prog_begin and rc_prog_end the entry points above (on the calling thread) append to a program
- * instead of launching; every buffer they name must stay allocated for as long as the program is run.
- * rc_prog_lane(1) marks the following calls as off the critical path: they may run concurrently with the
- * lane-0 calls recorded after them (lane-1 calls stay ordered among themselves and after all earlier lane-0 calls).
- * rc_prog_end uploads the program into device_buf (rc_prog_bytes() bytes) and fills
- * info = {n_ops, n_phases, dynamic shared memory bytes, offset of the phase table}.
- * rc_prog_run launches it (cooperative launch, one CTA pair per SM, grid-wide barrier between phases). */
-int rc_prog_begin(void);
-int rc_prog_lane(int lane);
-int rc_prog_join(void);   /* later lane-0 calls wait for every lane-1 call recorded so far */
-int rc_prog_abort(void);
-int rc_prog_nop(void);    /* records an empty phase (one grid-wide barrier): for measuring the barrier cost */
-size_t rc_prog_bytes(void);
-int rc_prog_end(void* device_buf, size_t bytes, int* info /* [4], host */);
-int rc_prog_run(const void* device_buf, const int* info /* [4], host */, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

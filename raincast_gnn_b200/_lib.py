@@ -99,14 +99,6 @@ def _declare(lib):
         "rc_gather_dates": (i, [p, p, p, p, i, i, ll, ll, ll, p, p, p, p, p]),
         "rc_p2p_barrier": (i, [p, p, i, i, i, p, p]),
         "rc_p2p_adamw_step": (i, [p, p, i, p, p, p, ll, f, f, f, f, f, p]),
-        "rc_prog_begin": (i, []),
-        "rc_prog_lane": (i, [i]),
-        "rc_prog_join": (i, []),
-        "rc_prog_abort": (i, []),
-        "rc_prog_nop": (i, []),
-        "rc_prog_bytes": (sz, []),
-        "rc_prog_end": (i, [p, sz, C.POINTER(C.c_int)]),
-        "rc_prog_run": (i, [p, C.POINTER(C.c_int), p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

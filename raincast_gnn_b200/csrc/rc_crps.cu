@@ -3,7 +3,6 @@
 // (models/model_utils.py:89-113, models/loss.py:203-272).
 
 #include "rc_crps_tile.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -108,11 +107,6 @@ extern "C" int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred,
   const CrpsCountP pc{y, m, ws.cnt};
   const CrpsMainP pm{pred, y, d_pred, m, kind, raw_input, u_fixed, xi, t, ws.cnt, ncnt, ws.loss};
   const CrpsFinalP pf{ws.cnt, ncnt, ws.loss, blocks, loss_out, n_valid};
-  if (recording()) {
-    if (int e = record_op(OP_CRPS_COUNT, 0, dim3(ncnt), 0, &pc, sizeof(pc))) return e;
-    if (int e = record_op(OP_CRPS_MAIN, kind, dim3(blocks), 0, &pm, sizeof(pm))) return e;
-    return record_op(OP_CRPS_FINAL, 0, dim3(1), 0, &pf, sizeof(pf));
-  }
   if (m > 0 && m <= 1024) {
     const CrpsSmallP ps{pm, loss_out, n_valid};
     switch (kind) {
@@ -139,7 +133,6 @@ extern "C" int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred,
 extern "C" int rc_postprocess_fwd(const float* raw, float* post, int num_nodes, int kind, void* stream) {
   if (!raw || !post || kind < 0 || kind > 3) return fail(RC_ERR_ARG, "rc_postprocess_fwd: bad argument");
   if (num_nodes == 0) return RC_OK;
-  if (recording()) return fail(RC_ERR_ARG, "rc_postprocess_fwd cannot be recorded into a step program");
   postprocess_fwd_kernel<<<ceil_div(num_nodes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(PostFwdP{raw, post, num_nodes, kind});
   return check_launch("postprocess_fwd_kernel");
 }
@@ -147,7 +140,6 @@ extern "C" int rc_postprocess_fwd(const float* raw, float* post, int num_nodes, 
 extern "C" int rc_postprocess_bwd(const float* raw, const float* d_post, float* d_raw, int num_nodes, int kind, void* stream) {
   if (!raw || !d_post || !d_raw || kind < 0 || kind > 3) return fail(RC_ERR_ARG, "rc_postprocess_bwd: bad argument");
   if (num_nodes == 0) return RC_OK;
-  if (recording()) return fail(RC_ERR_ARG, "rc_postprocess_bwd cannot be recorded into a step program");
   postprocess_bwd_kernel<<<ceil_div(num_nodes, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(PostBwdP{raw, d_post, d_raw, num_nodes, kind});
   return check_launch("postprocess_bwd_kernel");
 }

@@ -5,7 +5,6 @@
 // [M*Em, H] is written to HBM.  fp32 FFMA; the member rows of a station are staged in shared memory.
 
 #include "rc_deepsets_tile.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -46,7 +45,6 @@ extern "C" int rc_deepsets_pool_fwd(const float* ens, const float* w1, const flo
   if (gx > 4 * kNumSMs) gx = 4 * kNumSMs;
   dim3 grid(gx, ceil_div(hidden, kDsCols));
   const DsFwdP p{ens, w1, b1, pooled, num_nodes, members, feats, hidden, f4};
-  if (recording()) return record_op(OP_DS_FWD, 0, grid, smem, &p, sizeof(p));
   launch_pdl(deepsets_pool_fwd_kernel, grid, dim3(kDsThreads), smem, static_cast<cudaStream_t>(stream), p);
   return check_launch("deepsets_pool_fwd_kernel");
 }
@@ -56,7 +54,6 @@ extern "C" int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, cons
   if (!ens || !w1 || !b1 || !pooled || num_nodes < 0 || members <= 0 || feats <= 0 || hidden <= 0)
     return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd_bf16: bad argument");
   if (members > 128 || feats > 64) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd_bf16: needs members <= 128 and feats <= 64");
-  if (recording()) return fail(RC_ERR_ARG, "rc_deepsets_pool_fwd_bf16 cannot be recorded into a step program");
   if (num_nodes == 0) return RC_OK;
   return launch_deepsets_fwd_tc(true, ens, w1, b1, pooled, num_nodes, members, feats, hidden, static_cast<cudaStream_t>(stream));
 }
@@ -78,7 +75,6 @@ static int ds_bwd_launch(const float* ens, const float* w1, const float* b1, con
   }
   dim3 grid(ds_bwd_blocks(m), ceil_div(hidden, kDsCols));
   const DsBwdP p{ens, w1, b1, d_pooled, partials, m, members, feats, hidden, bf16_operands};
-  if (recording()) return record_op(OP_DS_BWD, KQ, grid, smem, &p, sizeof(p));
   launch_pdl(deepsets_pool_bwd_kernel<KQ>, grid, dim3(kDsThreads), smem, s, p);
   return check_launch("deepsets_pool_bwd_kernel");
 }

@@ -17,7 +17,6 @@
 #include <stdlib.h>
 
 #include "rc_common.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -337,7 +336,7 @@ bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden) {
     forced = e ? (atoi(e) ? 1 : 2) : 0;                 // 1 = always when legal, 2 = never, 0 = by size
   }
   const bool legal = members >= 1 && members <= kTcRows && feats >= 1 && feats <= 64 && hidden >= 1;
-  if (!legal || forced == 2 || recording()) return false;
+  if (!legal || forced == 2) return false;
   if (forced == 1) return true;
   return (long long)num_nodes * members >= 65536 && hidden % 128 == 0;
 }

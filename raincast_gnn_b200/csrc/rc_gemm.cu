@@ -11,7 +11,6 @@
 // double-buffered global loads, one __syncthreads per slice).  Per 4 reduction steps a thread issues
 // RM + 4 LDS.128 for 16*RM FFMA, which is FFMA-bound for RM = 8.
 #include "rc_gemm_tile.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -48,10 +47,6 @@ static int gemm_launch(const GemmP& p, dim3 grid, cudaStream_t s) {
   const int slices = p.tiles1 + p.tiles2;
   const int per_cta = p.g.splits > 1 ? ceil_div(slices, p.g.splits) : slices;
   const size_t smem = gemm_smem_bytes<RM, AL, BL, kRK>(per_cta > 1 ? 2 : 1);
-  if (recording()) {
-    if (RM > 4) return fail(RC_ERR_ARG, "rc_gemm_run: this tile shape is not part of the step program");
-    return record_op(OP_GEMM, RM | (AL << 4) | (BL << 5) | ((kRK == 128) << 6), grid, smem, &p, sizeof(p));
-  }
   if (!attr_set) {
     cudaFuncSetAttribute(gemm_kernel<RM, AL, BL, kRK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)gemm_smem_bytes<RM, AL, BL, kRK>(2));

@@ -7,7 +7,6 @@
 // load and nothing of size [E, H] is ever materialised (the reference materialises four).
 // HBM-bound kernel: algorithmic bytes fwd = 2*M*H*4 + E*8 + (M+1)*4 + 8*H  (SURVEY.md 8d).
 #include "rc_gine_tile.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -44,10 +43,9 @@ extern "C" int rc_gine_aggr_fwd(const float* x, const int32_t* rowptr, const int
   if (num_nodes == 0) return RC_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool ranged = sh.lpr == 32 && num_nodes >= kRangedMinRows;
-  if (ranged && !recording()) return launch_gine_fwd_ranged(x, rowptr, col, attr, w_edge, b_edge, eps, h, num_nodes, hidden, s);
+  if (ranged) return launch_gine_fwd_ranged(x, rowptr, col, attr, w_edge, b_edge, eps, h, num_nodes, hidden, s);
   const int grid = ceil_div(num_nodes, kGineWarps * sh.rpw);
   const GineFwdP p{x, rowptr, col, attr, w_edge, b_edge, eps, h, num_nodes, hidden, sh.lpr};
-  if (recording()) return record_op(OP_GINE_FWD, sh.ch, dim3(grid), 0, &p, sizeof(p));
   switch (sh.ch) {
     case 1: launch_pdl(gine_aggr_fwd_kernel<1>, dim3(grid), dim3(kGineThreads), 0, s, p); break;
     case 2: launch_pdl(gine_aggr_fwd_kernel<2>, dim3(grid), dim3(kGineThreads), 0, s, p); break;
@@ -66,7 +64,7 @@ static int gine_small_blocks(int num_nodes, const GineShape& sh) {
 extern "C" int rc_gine_aggr_bwd_nblocks(int num_nodes, int hidden) {
   GineShape sh;
   if (!gine_shape(hidden, &sh) || num_nodes < 0) return -1;
-  if (sh.lpr == 32 && num_nodes >= kRangedMinRows && !recording()) return gine_ranged_grid(num_nodes);
+  if (sh.lpr == 32 && num_nodes >= kRangedMinRows) return gine_ranged_grid(num_nodes);
   return gine_small_blocks(num_nodes, sh);
 }
 
@@ -81,13 +79,12 @@ extern "C" int rc_gine_aggr_bwd(const float* g, const float* x, const int32_t* t
       (addend && !aligned16(addend)))
     return fail(RC_ERR_ARG, "rc_gine_aggr_bwd: g, x, dx, addend, w_edge, b_edge, partials must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (sh.lpr == 32 && num_nodes >= kRangedMinRows && !recording())
+  if (sh.lpr == 32 && num_nodes >= kRangedMinRows)
     return launch_gine_bwd_ranged(g, x, t_rowptr, t_dst, t_attr, w_edge, b_edge, eps, addend, dx, partials, num_nodes, hidden, s);
   const int grid = gine_small_blocks(num_nodes, sh);
   const int rpb = kGineWarps * sh.rpw;
   const size_t smem = ((size_t)rpb * 2 * hidden + rpb) * sizeof(float);
   const GineBwdP p{g, x, t_rowptr, t_dst, t_attr, w_edge, b_edge, eps, addend, dx, partials, num_nodes, hidden, sh.lpr};
-  if (recording()) return record_op(OP_GINE_BWD, sh.ch, dim3(grid), smem, &p, sizeof(p));
 #define RC_LAUNCH_BWD(CHV)                                                                                                  \
   do {                                                                                                                      \
     if (smem > 48 * 1024) cudaFuncSetAttribute(gine_aggr_bwd_kernel<CHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -108,7 +105,6 @@ extern "C" int rc_gine_aggr_bwd_finalize(const float* partials, int nblocks, int
   if (!partials || !d_w || !d_b || !d_eps || nblocks < 0 || hidden <= 0) return fail(RC_ERR_ARG, "rc_gine_aggr_bwd_finalize: bad argument");
   const int grid = ceil_div(2 * hidden, 32) + 1;
   const GineFinP p{partials, nblocks, hidden, d_w, d_b, d_eps};
-  if (recording()) return record_op(OP_GINE_FIN, 0, dim3(grid), 0, &p, sizeof(p));
   launch_pdl(gine_bwd_finalize_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("gine_bwd_finalize_kernel");
 }

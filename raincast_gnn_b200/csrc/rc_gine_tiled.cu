@@ -27,7 +27,6 @@
 // Backward: the transpose tiles stage g rows; the ReLU mask is recomputed from the row's own x and the edge attr
 // (nothing per-edge saved); d w_edge / d b_edge / d eps partials per CTA, same format as rc_gine_aggr_bwd.
 #include "rc_common.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -494,7 +493,6 @@ extern "C" int rc_gine_aggr_fwd_tiled(const float* x, const rc_gine_tiles* tiles
                                       const float* eps, float* h, int num_nodes, int hidden, void* stream) {
   if (!x || !w_edge || !b_edge || !eps || !h || num_nodes < 0) return fail(RC_ERR_ARG, "rc_gine_aggr_fwd_tiled: null pointer");
   if (int rc = check_tiles(tiles, hidden, "rc_gine_aggr_fwd_tiled")) return rc;
-  if (recording()) return fail(RC_ERR_ARG, "rc_gine_aggr_fwd_tiled: not available inside a step program (large-graph path)");
   if (!aligned16(x) || !aligned16(h) || !aligned16(w_edge) || !aligned16(b_edge))
     return fail(RC_ERR_ARG, "rc_gine_aggr_fwd_tiled: x, h, w_edge, b_edge must be 16-byte aligned");
   if (num_nodes == 0 || tiles->n_tiles == 0) return RC_OK;
@@ -519,7 +517,6 @@ extern "C" int rc_gine_aggr_bwd_tiled(const float* g, const float* x, const rc_g
                                       int num_nodes, int hidden, void* stream) {
   if (!g || !x || !w_edge || !b_edge || !eps || !dx || !partials || num_nodes < 0) return fail(RC_ERR_ARG, "rc_gine_aggr_bwd_tiled: null pointer");
   if (int rc = check_tiles(tiles, hidden, "rc_gine_aggr_bwd_tiled")) return rc;
-  if (recording()) return fail(RC_ERR_ARG, "rc_gine_aggr_bwd_tiled: not available inside a step program (large-graph path)");
   if (!aligned16(g) || !aligned16(x) || !aligned16(dx) || !aligned16(w_edge) || !aligned16(b_edge) || !aligned16(partials) ||
       (addend && !aligned16(addend)))
     return fail(RC_ERR_ARG, "rc_gine_aggr_bwd_tiled: g, x, dx, addend, w_edge, b_edge, partials must be 16-byte aligned");

@@ -2,7 +2,6 @@
 // reduction of every split gradient, and the fused AdamW update on flat buffers.
 
 #include "rc_misc_tile.cuh"
-#include "rc_prog.h"
 
 namespace rc {
 
@@ -89,7 +88,6 @@ extern "C" int rc_bn_stats_finalize(const float* stats, int row_tiles, int row_t
   if (row_tiles != ceil_div(m, row_tile)) return fail(RC_ERR_ARG, "rc_bn_stats_finalize: row_tiles %d != ceil(%d/%d)", row_tiles, m, row_tile);
   const BnStatsFinP p{stats, row_tiles, row_tile, m, n, eps, momentum, mean, rstd, running_mean, running_var,
                       reinterpret_cast<long long*>(num_batches_tracked)};
-  if (recording()) return record_op(OP_BN_STATS_FIN, 0, dim3(ceil_div(n, 32)), 0, &p, sizeof(p));
   launch_pdl(bn_stats_finalize_kernel, dim3(ceil_div(n, 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("bn_stats_finalize_kernel");
 }
@@ -98,7 +96,6 @@ extern "C" int rc_bn_eval_prepare(const float* running_mean, const float* runnin
                                   float* rstd, void* stream) {
   if (!running_mean || !running_var || !mean || !rstd || n <= 0) return fail(RC_ERR_ARG, "rc_bn_eval_prepare: bad argument");
   const BnEvalP p{running_mean, running_var, n, eps, mean, rstd};
-  if (recording()) return record_op(OP_BN_EVAL_PREP, 0, dim3(ceil_div(n, 256)), 0, &p, sizeof(p));
   bn_eval_prepare_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("bn_eval_prepare_kernel");
 }
@@ -109,7 +106,6 @@ extern "C" int rc_bn_bwd_finalize(const float* stats, int row_tiles, int m, int 
   if (!stats || !gamma || !mean || !rstd || !d_gamma || !d_beta || !c0 || !c1 || !c2 || row_tiles <= 0 || m <= 0 || n <= 0)
     return fail(RC_ERR_ARG, "rc_bn_bwd_finalize: bad argument");
   const BnBwdFinP p{stats, row_tiles, m, n, batch_stats, gamma, mean, rstd, d_gamma, d_beta, c0, c1, c2};
-  if (recording()) return record_op(OP_BN_BWD_FIN, 0, dim3(ceil_div(n, 32)), 0, &p, sizeof(p));
   launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(n, 32)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("bn_bwd_finalize_kernel");
 }
@@ -130,10 +126,6 @@ extern "C" int rc_reduce_segments(const rc_reduce_seg* segs, int n_segs, void* s
     if (max_n == 0) continue;
     int gx = ceil_div(max_n, 32);             // a CTA finishes 32 outputs per pass
     if (gx > 2 * kNumSMs) gx = 2 * kNumSMs;
-    if (recording()) {
-      if (int e = record_op(OP_REDUCE, 0, dim3(gx, cnt), 0, &args, sizeof(args))) return e;
-      continue;
-    }
     launch_pdl(reduce_segments_kernel, dim3(gx, cnt), dim3(256), 0, static_cast<cudaStream_t>(stream), args);
     if (int e = check_launch("reduce_segments_kernel")) return e;
   }
@@ -149,10 +141,6 @@ extern "C" int rc_adamw_step(float* param, const float* grad, float* exp_avg, fl
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
   const AdamTickP pt{reinterpret_cast<long long*>(step)};
   const AdamP pa{param, grad, exp_avg, exp_avg_sq, reinterpret_cast<long long*>(step), n, lr, beta1, beta2, eps, weight_decay, grad_scale};
-  if (recording()) {
-    if (int e = record_op(OP_ADAMW_TICK, 0, dim3(1), 0, &pt, sizeof(pt))) return e;
-    return n == 0 ? RC_OK : record_op(OP_ADAMW, 0, dim3((int)blocks), 0, &pa, sizeof(pa));
-  }
   launch_pdl(adamw_tick_kernel, dim3(1), dim3(32), 0, s, pt);
   if (int e = check_launch("adamw_tick_kernel")) return e;
   if (n == 0) return RC_OK;

@@ -46,7 +46,7 @@ def _flatten_into(tensors, flat):
 class TrainEngine:
     def __init__(self, model, graph: StationGraph, num_nodes: int, members: int, feats: int, *, lr: float = 1e-4,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None,
-                 use_cuda_graph: bool = True, mode: str = "graph"):
+                 use_cuda_graph: bool = True):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise _lib.RcError("TrainEngine needs the model on a CUDA device (there is no CPU path)")
@@ -90,13 +90,6 @@ class TrainEngine:
         self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         self._blocks = self._bind(model)
         self.use_cuda_graph = use_cuda_graph
-        # "graph" (default): CUDA graph of the separate kernels on two streams.
-        # "program": the same calls recorded into ONE persistent cooperative kernel with grid barriers (rc_prog_*).
-        #   Measured on B200 at the reference shape: 1.04 ms/step against 0.45 ms for the graph — the per-phase
-        #   dispatch (program table -> parameters -> data, all dependent global loads) costs more than a graph
-        #   node's launch gap, so it stays opt-in.  "auto": program when every op is part of it, else graph.
-        self.mode = mode
-        self._prog = None
         self._side = torch.cuda.Stream(device=dev)      # weight-gradient work overlaps the data-gradient chain
         # input prefetch: the next batch travels host -> staging buffers on a copy stream while the current step runs
         # In graph mode the staging buffers are a second input set with its own captured graph (same kernels, same
@@ -218,41 +211,9 @@ class TrainEngine:
                                             self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world,
                                             torch.cuda.current_stream(self.device).cuda_stream), "rc_adamw_step")
 
-    def _record_program(self):
-        """Record fwd + loss + bwd (+ AdamW when there is no all-reduce in between) as a step program."""
-        import ctypes as C
-        L = _lib.lib()
-        _lib.check(L.rc_prog_begin(), "rc_prog_begin")
-        K.RECORD.active, K.RECORD.keep = True, []
-        try:
-            self._fwd_bwd_body()
-            K.join_side()
-            if self.world == 1:
-                self._adamw_call()
-            nbytes = int(L.rc_prog_bytes())
-            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            info = (C.c_int * 4)()
-            _lib.check(L.rc_prog_end(buf.data_ptr(), nbytes, info), "rc_prog_end")
-        except Exception:
-            L.rc_prog_abort()
-            raise
-        finally:
-            keep, K.RECORD.active, K.RECORD.keep = K.RECORD.keep, False, []
-        self._prog = (buf, info, keep)
-        self.kernels_per_step = 1
-        self.prog_ops, self.prog_phases = int(info[0]), int(info[1])
-
     def capture(self):
-        """Build the step: a step program (one persistent kernel) when possible, else warm up on a side stream and
-        capture fwd+bwd in a CUDA graph.  BatchNorm running statistics and Adam state are restored afterwards, so
-        capture has no training effect."""
-        if self.mode in ("auto", "program"):
-            try:
-                self._record_program()
-                return self
-            except _lib.RcError:
-                if self.mode == "program":
-                    raise
+        """Build the step: warm up on a side stream and capture fwd+bwd in a CUDA graph.  BatchNorm running statistics
+        and Adam state are restored afterwards, so capture has no training effect."""
         snap = {k: v.clone() for k, v in self.model.state_dict().items()}
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -348,30 +309,21 @@ class TrainEngine:
 
     def step(self):
         """One training step on the batch in the static buffers; returns the device-resident loss (float64 [1])."""
-        if self._prog is None and self._graph is None and self.use_cuda_graph:
+        if self._graph is None and self.use_cuda_graph:
             self.capture()
-        if self._prog is not None:
-            buf, info, _ = self._prog
-            _lib.check(_lib.lib().rc_prog_run(buf.data_ptr(), info, torch.cuda.current_stream(self.device).cuda_stream),
-                       "rc_prog_run")
-            if self.world > 1:
-                self._optimizer()
+        if self._graph is not None:
+            self._graph.replay()
+            if self._flipped:                         # the other input set may be refilled once this replay has run
+                self._stage_free.record(torch.cuda.current_stream(self.device))
+                self._flipped = False
         else:
-            if self._graph is not None:
-                self._graph.replay()
-                if self._flipped:                         # the other input set may be refilled once this replay has run
-                    self._stage_free.record(torch.cuda.current_stream(self.device))
-                    self._flipped = False
-            else:
-                self._fwd_bwd()
-            self._optimizer()
+            self._fwd_bwd()
+        self._optimizer()
         self.loss_sum.add_(self.loss)
         return self.loss
 
     @property
     def launches_per_step(self) -> int:
-        """librc kernel launches per step (program mode: the one persistent kernel, plus AdamW's two under DP)."""
+        """librc kernel launches per step."""
         opt = 4 if self.p2p is not None else 2        # barrier, tick, sum + AdamW, barrier  |  tick, AdamW
-        if self._prog is not None:
-            return 1 if self.world == 1 else 1 + opt
         return int(self.kernels_per_step or 0) + opt

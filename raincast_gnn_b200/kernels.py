@@ -40,21 +40,8 @@ class _Side:
 SIDE = _Side()
 
 
-class _Record:
-    """Step-program recording (rc_prog_*): while active, library calls append to a program instead of launching,
-    so every tensor they name must outlive the program — `keep` holds all buffers allocated here meanwhile."""
-    active = False
-    keep: list = []
-
-
-RECORD = _Record()
-
-
 def _new(shape, dtype=torch.float32, device=None):
-    t = torch.empty(shape, dtype=dtype, device=device)
-    if RECORD.active:
-        RECORD.keep.append(t)
-    return t
+    return torch.empty(shape, dtype=dtype, device=device)
 
 
 def _new_like(ref):
@@ -65,13 +52,6 @@ def _new_like(ref):
 def on_side(*inputs):
     """Run the enclosed launches on the side stream, ordered after everything issued so far on the current stream.
     `inputs` (tensors produced on the main stream and read here) are kept alive until join_side()."""
-    if RECORD.active:                      # step program: lane 1 = off the critical path
-        _lib.check(_lib.lib().rc_prog_lane(1), "rc_prog_lane")
-        try:
-            yield
-        finally:
-            _lib.check(_lib.lib().rc_prog_lane(0), "rc_prog_lane")
-        return
     if SIDE.stream is None:
         yield
         return
@@ -84,9 +64,6 @@ def on_side(*inputs):
 
 
 def join_side():
-    if RECORD.active:
-        _lib.check(_lib.lib().rc_prog_join(), "rc_prog_join")
-        return
     if SIDE.stream is None:
         return
     ev = torch.cuda.Event()
@@ -254,7 +231,7 @@ def dimred_prepack(P, f, x=None):
     * with `x` (the batch's node features): xw = x @ wx^T + bias - the half of the Linear that does not need the
       DeepSets embedding - is computed here too, so that dimred_fwd on the critical path is one 128-long reduction
       slice that adds xw in its epilogue instead of two slices."""
-    if RECORD.active or SIDE.stream is None:
+    if SIDE.stream is None:
         return
     w = P["dimred_w"]
     n, ldw = w.shape
@@ -278,9 +255,9 @@ def dimred_prepack(P, f, x=None):
 
 
 def _dimred_pack(P, f):
-    """The aligned halves prepared for this step, or None (eager / step-program paths use the parameter directly)."""
+    """The aligned halves prepared for this step, or None (the eager path uses the parameter directly)."""
     pack = P.get("_dimred_pack")
-    if pack is None or pack.get("ready") is None or pack["f"] != f or RECORD.active:
+    if pack is None or pack.get("ready") is None or pack["f"] != f:
         return None
     return pack
 

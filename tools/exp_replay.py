@@ -10,7 +10,7 @@ dev = torch.device("cuda:0")
 ei, ea, ei_b, ea_b = B.static_graph(8)
 m = 8 * B.N_STATIONS
 sg = build_station_graph(ei_b, ea_b, m).to(dev)
-eng = TrainEngine(B.seeded_model(GNN).to(dev).train(), sg, m, B.MEMBERS, B.FEATS, mode="graph").capture()
+eng = TrainEngine(B.seeded_model(GNN).to(dev).train(), sg, m, B.MEMBERS, B.FEATS).capture()
 x, ens = syn.node_features(m, B.MEMBERS, B.FEATS, seed=1); y = syn.log_precip_targets(m, seed=1)
 eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
 for _ in range(10): eng._graph.replay()

@@ -95,7 +95,7 @@ def big_step(hidden, em, bf16, n=100_000):
     model.to(dev).train()
     if bf16:
         model.deepset.compute_dtype = "bf16"
-    eng = TrainEngine(model, sg, n, em, B.FEATS, use_cuda_graph=False, mode="graph")
+    eng = TrainEngine(model, sg, n, em, B.FEATS, use_cuda_graph=False)
     x, ens = syn.node_features(n, em, B.FEATS, seed=3)
     y = syn.log_precip_targets(n, seed=3)
     eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))

@@ -17,7 +17,7 @@ sg = G.build_station_graph(ei, ea, n).to(dev)
 x, ens = syn.node_features(n, em, B.FEATS, seed=3)
 y = syn.log_precip_targets(n, seed=3)
 model = B.seeded_model(GNN).to(dev).train()
-eng = TrainEngine(model, sg, n, em, B.FEATS, use_cuda_graph=False, mode="graph")
+eng = TrainEngine(model, sg, n, em, B.FEATS, use_cuda_graph=False)
 eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
 blk = eng._blocks
 
