@@ -204,9 +204,17 @@ typedef struct rc_gemm {
   int splits; long long split_stride;
   float* colsum_a;
   int rows_per_warp;          /* 0 = choose; else 1, 2, 4 or 8 (row tile = 8 * rows_per_warp) */
+  /* tensor-core path (tcgen05, 3xTF32: fp32-accurate): taken for activation GEMMs (A stored [i][r]) with m >= 16384
+   * when tc_ws holds rc_gemm_tc_workspace(g) bytes (the pre-split weight blocks live there for the duration of the
+   * call), and for weight-gradient GEMMs (A stored [r][i], B stored [r][j]) with k >= 16384 samples (no workspace).
+   * RC_GEMM_TC=0 in the environment keeps everything on the SIMT kernels. */
+  void* tc_ws; size_t tc_ws_bytes;
 } rc_gemm;
 
 int rc_gemm_row_tile(const rc_gemm* g);  /* the row tile the launch would use (for stats sizing)   */
+size_t rc_gemm_tc_workspace(const rc_gemm* g);   /* 0: the tensor-core path does not apply to this activation GEMM */
+/* reduction splits the tensor-core weight-gradient kernel wants for D (m x n) over k samples; 0: not applicable */
+int rc_gemm_tc_wgrad_splits(int m, int n, int k);
 int rc_gemm_run(const rc_gemm* g, void* stream);
 
 /* BatchNorm1d training-mode statistics from the RC_EPI_BN_STATS tiles (per-tile count / mean / M2 combined in

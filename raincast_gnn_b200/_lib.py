@@ -47,7 +47,7 @@ class rc_gemm(C.Structure):
                 ("res", _fp), ("ld_res", C.c_int), ("bits_out", _fp), ("ld_bits_out", C.c_int),
                 ("e_aux", _fp), ("ld_e_aux", C.c_int), ("e_p0", _fp), ("e_p1", _fp), ("e_p2", _fp), ("e_p3", _fp),
                 ("stats", _fp), ("splits", C.c_int), ("split_stride", C.c_longlong), ("colsum_a", _fp),
-                ("rows_per_warp", C.c_int)]
+                ("rows_per_warp", C.c_int), ("tc_ws", _fp), ("tc_ws_bytes", C.c_size_t)]
 
 
 class rc_reduce_seg(C.Structure):
@@ -83,6 +83,8 @@ def _declare(lib):
         "rc_gine_aggr_bwd_tiled": (i, [p, p, C.POINTER(rc_gine_tiles), p, p, p, p, p, p, i, i, p]),
         "rc_gemm_row_tile": (i, [C.POINTER(rc_gemm)]),
         "rc_gemm_run": (i, [C.POINTER(rc_gemm), p]),
+        "rc_gemm_tc_workspace": (sz, [C.POINTER(rc_gemm)]),
+        "rc_gemm_tc_wgrad_splits": (i, [i, i, i]),
         "rc_bn_stats_finalize": (i, [p, i, i, i, i, f, f, p, p, p, p, p, p]),
         "rc_bn_eval_prepare": (i, [p, p, i, f, p, p, p]),
         "rc_bn_bwd_finalize": (i, [p, i, i, i, i, p, p, p, p, p, p, p, p, p]),

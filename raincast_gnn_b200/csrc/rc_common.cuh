@@ -90,4 +90,12 @@ bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden);
 int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
                            int members, int feats, int hidden, cudaStream_t s);
 
+
+// rc_gemm_tc.cu: tcgen05 3xTF32 path of rc_gemm_run (1 = activation rows, 2 = weight gradient, 0 = not applicable)
+int gemm_tc_kind(const rc_gemm* g);
+size_t gemm_tc_workspace(const rc_gemm* g);
+int gemm_tc_wgrad_splits(const rc_gemm* g);
+int gemm_tc_run(const rc_gemm* g, cudaStream_t s);
+void gemm_tc_set_trace(long long* p);
+
 }  // namespace rc

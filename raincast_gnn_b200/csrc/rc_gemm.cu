@@ -94,7 +94,20 @@ using namespace rc;
 
 extern "C" int rc_gemm_row_tile(const rc_gemm* g) {
   if (!g) return -1;
+  if (g->tc_ws && gemm_tc_kind(g) == 1) return 64;     // statistics tiles of the tensor-core kernel: half a 128-row tile
   return 8 * choose_rm(g);
+}
+
+/* debug: device buffer of 3 x 16 x 2 int64; CTA 0 of the tensor-core rows kernel records, for its first 16 tiles, the
+ * clock at which its producer / MMA / epilogue role began and ended the tile (NULL switches it off) */
+extern "C" void rc_debug_tc_trace(void* device_buf) { gemm_tc_set_trace(static_cast<long long*>(device_buf)); }
+
+extern "C" size_t rc_gemm_tc_workspace(const rc_gemm* g) { return g ? gemm_tc_workspace(g) : 0; }
+
+extern "C" int rc_gemm_tc_wgrad_splits(int m, int n, int k) {
+  rc_gemm g = {};
+  g.m = m; g.n = n; g.k = k; g.a_layout = RC_A_RED; g.b_layout = RC_B_RED;
+  return gemm_tc_kind(&g) == 2 ? gemm_tc_wgrad_splits(&g) : 0;
 }
 
 extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
@@ -112,6 +125,10 @@ extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
   if (g->splits > 1 && g->bias) return fail(RC_ERR_ARG, "rc_gemm_run: split reduction cannot add a bias");
   if (g->colsum_a && g->a_layout != RC_A_RED) return fail(RC_ERR_ARG, "rc_gemm_run: colsum_a needs A stored [r][i]");
   if (g->m == 0 || g->n == 0) return RC_OK;
+  {
+    const int tc = gemm_tc_kind(g);
+    if ((tc == 1 && g->tc_ws) || tc == 2) return gemm_tc_run(g, static_cast<cudaStream_t>(stream));
+  }
   GemmP p;
   p.g = *g;
   auto vec_ok = [](const float* ptr, int ld) { return ptr != nullptr && (ld % 4 == 0) && aligned16(ptr); };

@@ -84,15 +84,24 @@ def gemm(m, n, k, a: _lib.rc_operand, b: _lib.rc_operand, d, ldd, *, a_layout=RC
     g = _lib.rc_gemm(m, n, k, a_layout, b_layout, a, b, _lib.ptr(a2), lda2, _lib.ptr(b2), ldb2, k2, _lib.ptr(d), ldd,
                      _lib.ptr(bias), bias_scale, epi, _lib.ptr(res), ld_res, _lib.ptr(bits_out), ld_bits_out,
                      _lib.ptr(e_aux), ld_e_aux, _lib.ptr(e_p[0]), _lib.ptr(e_p[1]), _lib.ptr(e_p[2]), _lib.ptr(e_p[3]),
-                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp)
+                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp, None, 0)
     if run:
-        _lib.check(_lib.lib().rc_gemm_run(C.byref(g), _stream(d)), "rc_gemm_run")
+        L = _lib.lib()
+        ws_bytes = int(L.rc_gemm_tc_workspace(C.byref(g)))     # > 0: large activation GEMM -> tensor cores (3xTF32)
+        if ws_bytes:
+            ws = _new(ws_bytes, torch.uint8, d.device)          # pre-split weight blocks, needed for this call only
+            g.tc_ws, g.tc_ws_bytes = ws.data_ptr(), ws_bytes
+        _lib.check(L.rc_gemm_run(C.byref(g), _stream(d)), "rc_gemm_run")
     return g
 
 
-def gemm_row_tile(m, n, splits=1) -> int:
+def gemm_row_tile(m, n, k=0) -> int:
+    """Rows per statistics tile of the forward GEMM gemm() would launch for an m x n output over k."""
     g = _lib.rc_gemm()
-    g.m, g.n, g.splits = m, n, splits
+    g.m, g.n, g.k, g.splits = m, n, k, 1
+    g.a_layout, g.b_layout = RC_A_ROW, RC_B_COL
+    if k and int(_lib.lib().rc_gemm_tc_workspace(C.byref(g))):
+        return 64
     return int(_lib.lib().rc_gemm_row_tile(C.byref(g)))
 
 
@@ -156,7 +165,7 @@ def linear_bwd_weight(dy_op: _lib.rc_operand, x_op: _lib.rc_operand, m, n, k, dw
     """dw[N, k] = dy^T @ x (+ db[N] = bias_scale * column sums of dy).  dy stored [M,N], x stored [M,k].
     `dw` may be a column block of a wider matrix (dw_ld = its row stride)."""
     dev = dw.device
-    splits = choose_splits(m, n, k)
+    splits = int(_lib.lib().rc_gemm_tc_wgrad_splits(n, k, m)) or choose_splits(m, n, k)
     dw_ld = k if dw_ld is None else dw_ld
     direct = splits == 1 and dw_ld == k and bias_scale == 1.0
     if direct:
@@ -360,7 +369,7 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     if training:
         if m < 2:
             raise ValueError("Expected more than 1 value per channel when training (BatchNorm1d)")
-        row_tile = gemm_row_tile(m, hid)
+        row_tile = gemm_row_tile(m, hid, h)
         tiles = math.ceil(m / row_tile)
         stats = _new((tiles, 2, hid), torch.float32, dev)
         gemm(m, hid, h, operand(agg, h), operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"], epi=RC_EPI_BN_STATS, stats=stats)
@@ -397,7 +406,7 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
         linear_bwd_weight(do_op, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), m, out_dim, hid,
                           G["nn3_w"], G["nn3_b"], sink)
     # d z = (d o @ W2) * 1[BN(t) > 0], with the two BatchNorm column reductions in the epilogue
-    row_tile = gemm_row_tile(m, hid)
+    row_tile = gemm_row_tile(m, hid, out_dim)
     tiles = math.ceil(m / row_tile)
     stats = _new((tiles, 2, hid), torch.float32, dev)
     dz = _new((m, hid), torch.float32, dev)
