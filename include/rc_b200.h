@@ -260,11 +260,14 @@ int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, const float* b1
                               int members, int feats, int hidden, void* stream);
 /* d w1 / d b1 partials from d pooled (ReLU mask recomputed, nothing saved in forward):
  * partials[nblocks][H*F + H]. */
-int rc_deepsets_pool_bwd_nblocks(int num_nodes, int hidden);
+int rc_deepsets_pool_bwd_nblocks(int num_nodes, int members, int feats, int hidden);
+/* With num_nodes*members >= 65536 and 11 or 51 members (the reference's ensembles) the backward also runs on the tensor
+ * cores (tcgen05, 3xTF32; RC_DEEPSETS_TC=0/1 overrides).  mask_bits_out (nullable, tests): the ReLU mask the backward
+ * used, bit (c % 32) of word [row * ceil(H/32) + c / 32] for member row `row`, channel c - tensor-core path only. */
 int rc_deepsets_pool_bwd(const float* ens, const float* w1, const float* b1, const float* d_pooled,
                          float* partials, int num_nodes, int members, int feats, int hidden,
                          int bf16_operands /* 1 after rc_deepsets_pool_fwd_bf16: mask and inputs as the tensor cores saw them */,
-                         void* stream);
+                         uint32_t* mask_bits_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Output links + closed-form CRPS (models/model_utils.py:70-113, models/loss.py:6-68,71-272,335-369)

@@ -91,8 +91,8 @@ def _declare(lib):
         "rc_reduce_segments": (i, [C.POINTER(rc_reduce_seg), i, p]),
         "rc_deepsets_pool_fwd": (i, [p, p, p, p, i, i, i, i, p]),
         "rc_deepsets_pool_fwd_bf16": (i, [p, p, p, p, i, i, i, i, p]),
-        "rc_deepsets_pool_bwd_nblocks": (i, [i, i]),
-        "rc_deepsets_pool_bwd": (i, [p, p, p, p, p, i, i, i, i, i, p]),
+        "rc_deepsets_pool_bwd_nblocks": (i, [i, i, i, i]),
+        "rc_deepsets_pool_bwd": (i, [p, p, p, p, p, i, i, i, i, i, p, p]),
         "rc_postprocess_fwd": (i, [p, p, i, i, p]),
         "rc_postprocess_bwd": (i, [p, p, p, i, i, p]),
         "rc_crps_workspace": (sz, [i]),

@@ -91,6 +91,12 @@ int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const f
                            int members, int feats, int hidden, cudaStream_t s);
 
 
+// rc_deepsets_tc_bwd.cu: tcgen05 / TMEM path of the DeepSets pool backward (members 11 / 51)
+bool deepsets_bwd_tc_applicable(int num_nodes, int members, int feats, int hidden);
+int deepsets_bwd_tc_blocks(int num_nodes, int members);
+int launch_deepsets_bwd_tc(const float* ens, const float* w1, const float* b1, const float* d_pooled, float* partials,
+                           uint32_t* mask_out, int num_nodes, int members, int feats, int hidden, int bf16, cudaStream_t s);
+
 // rc_gemm_tc.cu: tcgen05 3xTF32 path of rc_gemm_run (1 = activation rows, 2 = weight gradient, 0 = not applicable)
 int gemm_tc_kind(const rc_gemm* g);
 size_t gemm_tc_workspace(const rc_gemm* g);

@@ -58,8 +58,9 @@ extern "C" int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, cons
   return launch_deepsets_fwd_tc(true, ens, w1, b1, pooled, num_nodes, members, feats, hidden, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int rc_deepsets_pool_bwd_nblocks(int num_nodes, int hidden) {
-  if (num_nodes < 0 || hidden <= 0) return -1;
+extern "C" int rc_deepsets_pool_bwd_nblocks(int num_nodes, int members, int feats, int hidden) {
+  if (num_nodes < 0 || hidden <= 0 || members <= 0 || feats <= 0) return -1;
+  if (deepsets_bwd_tc_applicable(num_nodes, members, feats, hidden)) return deepsets_bwd_tc_blocks(num_nodes, members);
   return ds_bwd_blocks(num_nodes);
 }
 
@@ -81,11 +82,14 @@ static int ds_bwd_launch(const float* ens, const float* w1, const float* b1, con
 
 extern "C" int rc_deepsets_pool_bwd(const float* ens, const float* w1, const float* b1, const float* d_pooled,
                                     float* partials, int num_nodes, int members, int feats, int hidden, int bf16_operands,
-                                    void* stream) {
+                                    uint32_t* mask_bits_out, void* stream) {
   if (!ens || !w1 || !b1 || !d_pooled || !partials || num_nodes < 0 || members <= 0 || feats <= 0 || hidden <= 0)
     return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: bad argument");
   if (!aligned16(d_pooled)) return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: d_pooled must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (num_nodes > 0 && deepsets_bwd_tc_applicable(num_nodes, members, feats, hidden))
+    return launch_deepsets_bwd_tc(ens, w1, b1, d_pooled, partials, mask_bits_out, num_nodes, members, feats, hidden, bf16_operands, s);
+  if (mask_bits_out) return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: the mask dump is implemented on the tensor-core path only (RC_DEEPSETS_TC=1, 11 or 51 members)");
   const int kq = ceil_div(feats, 8);
   switch (kq) {
     case 1: return ds_bwd_launch<1>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);

@@ -200,7 +200,7 @@ def deepsets_fwd(P, ens, bf16: bool = False):
     return emb, (ens, pooled, s2, r1, bf16)
 
 
-def deepsets_bwd(P, saved, d_emb, G):
+def deepsets_bwd(P, saved, d_emb, G, mask_out=None):
     ens, pooled, s2, r1, bf16 = saved
     m, em, f = ens.shape
     h = P["phi0_w"].shape[0]
@@ -221,10 +221,10 @@ def deepsets_bwd(P, saved, d_emb, G):
         linear_bwd_weight(operand(d_s2, h), operand(pooled, h), m, h, h, G["phi2_w"], G["phi2_b"], sink, bias_scale=float(em))
     d_pooled = linear_bwd_data(d_s2, P["phi2_w"])
     # phi[0] + ReLU, per member
-    nb = int(L.rc_deepsets_pool_bwd_nblocks(m, h))
+    nb = int(L.rc_deepsets_pool_bwd_nblocks(m, em, f, h))
     part = _new((nb, h * f + h), torch.float32, dev)
     _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), d_pooled.data_ptr(),
-                                      part.data_ptr(), m, em, f, h, int(bf16), _stream(ens)), "rc_deepsets_pool_bwd")
+                                      part.data_ptr(), m, em, f, h, int(bf16), _lib.ptr(mask_out), _stream(ens)), "rc_deepsets_pool_bwd")
     sink.add(part, G["phi0_w"], h * f + h, nb, h * f)
     sink.add(part.reshape(-1)[h * f:], G["phi0_b"], h * f + h, nb, h)
     with on_side(part):

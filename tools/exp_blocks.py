@@ -83,9 +83,9 @@ L = _lib.lib()
 ens_, pooled, s2, r1, bf16 = s_ds
 em, f, hdim = ens_.shape[1], ens_.shape[2], Pd["phi0_w"].shape[0]
 d_pooled = torch.randn(m, hdim, device=dev)
-nb = int(L.rc_deepsets_pool_bwd_nblocks(m, hdim))
+nb = int(L.rc_deepsets_pool_bwd_nblocks(m, em, f, hdim))
 part = torch.empty(nb, hdim * f + hdim, device=dev)
-chain("  pool_bwd kernel", lambda: _lib.check(L.rc_deepsets_pool_bwd(ens_.data_ptr(), Pd["phi0_w"].data_ptr(), Pd["phi0_b"].data_ptr(), d_pooled.data_ptr(), part.data_ptr(), m, em, f, hdim, 0, torch.cuda.current_stream().cuda_stream)))
+chain("  pool_bwd kernel", lambda: _lib.check(L.rc_deepsets_pool_bwd(ens_.data_ptr(), Pd["phi0_w"].data_ptr(), Pd["phi0_b"].data_ptr(), d_pooled.data_ptr(), part.data_ptr(), m, em, f, hdim, 0, None, torch.cuda.current_stream().cuda_stream)))
 def red():
     sink = K.GradSink(dev)
     sink.add(part, Gd["phi0_w"], hdim * f + hdim, nb, hdim * f)

@@ -10,11 +10,11 @@ g = torch.Generator().manual_seed(0)
 ens = torch.randn(m, em, f, generator=g).to(dev)
 w1 = (torch.randn(h, f, generator=g) * 0.2).to(dev); b1 = torch.randn(h, generator=g).to(dev)
 dp = torch.randn(m, h, generator=g).to(dev)
-nb = int(L.rc_deepsets_pool_bwd_nblocks(m, h))
+nb = int(L.rc_deepsets_pool_bwd_nblocks(m, em, f, h))
 part = torch.empty(nb, h * f + h, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 def run():
-    _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), w1.data_ptr(), b1.data_ptr(), dp.data_ptr(), part.data_ptr(), m, em, f, h, 0, st))
+    _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), w1.data_ptr(), b1.data_ptr(), dp.data_ptr(), part.data_ptr(), m, em, f, h, 0, None, st))
 for _ in range(2): run()
 torch.cuda.synchronize()
 a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
