@@ -263,7 +263,7 @@ int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, const float* b1
 int rc_deepsets_pool_bwd_nblocks(int num_nodes, int members, int feats, int hidden);
 /* With num_nodes*members >= 65536 and 11 or 51 members (the reference's ensembles) the backward also runs on the tensor
  * cores (tcgen05, 3xTF32; RC_DEEPSETS_TC=0/1 overrides).  mask_bits_out (nullable, tests): the ReLU mask the backward
- * used, bit (c % 32) of word [row * ceil(H/32) + c / 32] for member row `row`, channel c - tensor-core path only. */
+ * used, bit (c % 32) of word [row * ceil(H/32) + c / 32] for member row `row`, channel c. */
 int rc_deepsets_pool_bwd(const float* ens, const float* w1, const float* b1, const float* d_pooled,
                          float* partials, int num_nodes, int members, int feats, int hidden,
                          int bf16_operands /* 1 after rc_deepsets_pool_fwd_bf16: mask and inputs as the tensor cores saw them */,
@@ -326,6 +326,21 @@ int rc_p2p_barrier(int32_t* const* flags, int32_t* epochs, int rank, int world, 
 int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, float* exp_avg, float* exp_avg_sq,
                       int64_t* step, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Test instrumentation: the ReLU decisions of the backward kernels as bit masks (bit c % 32 of word c / 32 per row).
+ * The parity tests force them into the float64 oracle so that gradients can be held to 1e-5 without an allowance for
+ * units within rounding of their threshold (tests/test_gpu_masked_parity.py).  Not used by the product path.
+ * ---------------------------------------------------------------------------------------------- */
+/* message ReLU of the GINE aggregation backward, per TRANSPOSE slot q (t_rowptr / t_attr of rc_csr): bits_out[E][ceil(H/32)];
+ * tiled = 1 evaluates the expression of rc_gine_aggr_bwd_tiled, 0 that of rc_gine_aggr_bwd */
+int rc_debug_gine_msg_mask(const float* x, const int32_t* t_rowptr, const float* t_attr, const float* w_edge,
+                           const float* b_edge, int num_nodes, int hidden, int tiled, uint32_t* bits_out, void* stream);
+/* ReLU behind BatchNorm as the RC_EPI_BN_RELU_BWD epilogue evaluates it: bits_out[m][ceil(n/32)] */
+int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          int m, int n, uint32_t* bits_out, void* stream);
+/* tensor-core GEMM timeline of CTA 0 (tools/trace_gemm_tc.py) */
+void rc_debug_tc_trace(void* device_buf);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,9 @@ def _declare(lib):
         "rc_gather_dates": (i, [p, p, p, p, i, i, ll, ll, ll, p, p, p, p, p]),
         "rc_p2p_barrier": (i, [p, p, i, i, i, p, p]),
         "rc_p2p_adamw_step": (i, [p, p, i, p, p, p, ll, f, f, f, f, f, p]),
+        "rc_debug_gine_msg_mask": (i, [p, p, p, p, p, i, i, i, p, p]),
+        "rc_debug_bn_relu_mask": (i, [p, i, p, p, p, p, i, i, p, p]),
+        "rc_debug_tc_trace": (None, [p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

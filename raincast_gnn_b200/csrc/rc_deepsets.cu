@@ -66,7 +66,7 @@ extern "C" int rc_deepsets_pool_bwd_nblocks(int num_nodes, int members, int feat
 
 template <int KQ>
 static int ds_bwd_launch(const float* ens, const float* w1, const float* b1, const float* d_pooled, float* partials, int m,
-                         int members, int feats, int hidden, int bf16_operands, cudaStream_t s) {
+                         int members, int feats, int hidden, int bf16_operands, uint32_t* mask_out, cudaStream_t s) {
   constexpr int FP = 8 * KQ;
   const size_t smem = ((size_t)FP * kDsCols + kDsCols + (size_t)64 * FP + (size_t)64 * kDsCols) * sizeof(float);
   static bool attr_set = false;
@@ -75,7 +75,7 @@ static int ds_bwd_launch(const float* ens, const float* w1, const float* b1, con
     attr_set = true;
   }
   dim3 grid(ds_bwd_blocks(m), ceil_div(hidden, kDsCols));
-  const DsBwdP p{ens, w1, b1, d_pooled, partials, m, members, feats, hidden, bf16_operands};
+  const DsBwdP p{ens, w1, b1, d_pooled, partials, m, members, feats, hidden, bf16_operands, mask_out};
   launch_pdl(deepsets_pool_bwd_kernel<KQ>, grid, dim3(kDsThreads), smem, s, p);
   return check_launch("deepsets_pool_bwd_kernel");
 }
@@ -89,17 +89,17 @@ extern "C" int rc_deepsets_pool_bwd(const float* ens, const float* w1, const flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (num_nodes > 0 && deepsets_bwd_tc_applicable(num_nodes, members, feats, hidden))
     return launch_deepsets_bwd_tc(ens, w1, b1, d_pooled, partials, mask_bits_out, num_nodes, members, feats, hidden, bf16_operands, s);
-  if (mask_bits_out) return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: the mask dump is implemented on the tensor-core path only (RC_DEEPSETS_TC=1, 11 or 51 members)");
+
   const int kq = ceil_div(feats, 8);
   switch (kq) {
-    case 1: return ds_bwd_launch<1>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 2: return ds_bwd_launch<2>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 3: return ds_bwd_launch<3>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 4: return ds_bwd_launch<4>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 5: return ds_bwd_launch<5>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 6: return ds_bwd_launch<6>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 7: return ds_bwd_launch<7>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
-    case 8: return ds_bwd_launch<8>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, s);
+    case 1: return ds_bwd_launch<1>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 2: return ds_bwd_launch<2>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 3: return ds_bwd_launch<3>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 4: return ds_bwd_launch<4>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 5: return ds_bwd_launch<5>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 6: return ds_bwd_launch<6>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 7: return ds_bwd_launch<7>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
+    case 8: return ds_bwd_launch<8>(ens, w1, b1, d_pooled, partials, num_nodes, members, feats, hidden, bf16_operands, mask_bits_out, s);
     default: return fail(RC_ERR_ARG, "rc_deepsets_pool_bwd: feats=%d > 64 is not instantiated", feats);
   }
 }

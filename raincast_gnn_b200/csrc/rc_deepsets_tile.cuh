@@ -29,6 +29,7 @@ struct DsBwdP {
   int feats;
   int hidden;
   int bf16_operands;   // forward ran with bf16 operands: recompute the ReLU mask (and use the inputs) as the tensor cores saw them
+  uint32_t* mask_out;  // test instrumentation (NULL in production): the ReLU mask used, bits [m*members][ceil(hidden/32)]
 };
 
 __device__ __forceinline__ float round_operand(float v, int bf16) {
@@ -286,6 +287,16 @@ __device__ __forceinline__ void ds_bwd_tile(const DsBwdP& p, const uint3 bid, co
           o.y = (acc[i][1] + bv.y > 0.f) ? d.y : 0.f;
           o.z = (acc[i][2] + bv.z > 0.f) ? d.z : 0.f;
           o.w = (acc[i][3] + bv.w > 0.f) ? d.w : 0.f;
+          if (p.mask_out != nullptr) {
+            // lane l holds columns 4l..4l+3 of the chunk: its nibble goes to bits 4*(l%8).. of word l/8
+            unsigned v = ((acc[i][0] + bv.x > 0.f) ? 1u : 0u) | ((acc[i][1] + bv.y > 0.f) ? 2u : 0u) |
+                         ((acc[i][2] + bv.z > 0.f) ? 4u : 0u) | ((acc[i][3] + bv.w > 0.f) ? 8u : 0u);
+            v <<= 4 * (lane & 7);
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            if ((lane & 7) == 0 && col < hidden) p.mask_out[(size_t)(row0 + r) * ((hidden + 31) / 32) + (col >> 5)] = v;
+          }
         }
         st4(dh + r * kDsCols + 4 * lane, o);
       }

@@ -40,6 +40,23 @@ class _Side:
 SIDE = _Side()
 
 
+class _MaskDump:
+    """Test instrumentation (include/rc_b200.h, "Test instrumentation"): while `active` is a dict, the backward blocks
+    record the ReLU decisions they take - "phi" (bits [M*Em, H/32]), "rho" (bool [M, H]) and, per GINE layer in the order
+    the backward visits them (last layer first), {"msg": bits per transpose slot, "bn": bits, "out": bits} under
+    "layers" - so that tests/test_gpu_masked_parity.py can force them into the float64 oracle."""
+    active = None
+
+
+MASKS = _MaskDump()
+
+
+def unpack_bits(bits, n):
+    """bits int32 [rows, ceil(n/32)] -> bool [rows, n]."""
+    words = bits.to(torch.int64) & 0xFFFFFFFF
+    return ((words.unsqueeze(-1) >> torch.arange(32, device=bits.device)) & 1).reshape(bits.shape[0], -1)[:, :n].bool()
+
+
 def _new(shape, dtype=torch.float32, device=None):
     return torch.empty(shape, dtype=dtype, device=device)
 
@@ -223,6 +240,10 @@ def deepsets_bwd(P, saved, d_emb, G, mask_out=None):
     # phi[0] + ReLU, per member
     nb = int(L.rc_deepsets_pool_bwd_nblocks(m, em, f, h))
     part = _new((nb, h * f + h), torch.float32, dev)
+    if MASKS.active is not None:
+        mask_out = torch.zeros((m * em, (h + 31) // 32), dtype=torch.int32, device=dev)
+        MASKS.active["phi"] = mask_out
+        MASKS.active["rho"] = r1 > 0
     _lib.check(L.rc_deepsets_pool_bwd(ens.data_ptr(), P["phi0_w"].data_ptr(), P["phi0_b"].data_ptr(), d_pooled.data_ptr(),
                                       part.data_ptr(), m, em, f, h, int(bf16), _lib.ptr(mask_out), _stream(ens)), "rc_deepsets_pool_bwd")
     sink.add(part, G["phi0_w"], h * f + h, nb, h * f)
@@ -426,6 +447,15 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
     # aggregation backward (+ residual branch of layers > 0)
     dx = _new((m, h), torch.float32, dev)
+    if MASKS.active is not None:
+        msg_bits = torch.zeros((graph.num_edges, (h + 31) // 32), dtype=torch.int32, device=dev)
+        bn_bits = torch.zeros((m, (hid + 31) // 32), dtype=torch.int32, device=dev)
+        _lib.check(L.rc_debug_gine_msg_mask(x.data_ptr(), graph.t_rowptr.data_ptr(), graph.t_attr.data_ptr(), P["lin_w"].data_ptr(),
+                                            P["lin_b"].data_ptr(), m, h, int(graph.tiles(h) is not None), msg_bits.data_ptr(), st),
+                   "rc_debug_gine_msg_mask")
+        _lib.check(L.rc_debug_bn_relu_mask(t.data_ptr(), hid, mean.data_ptr(), rstd.data_ptr(), P["bn_w"].data_ptr(),
+                                           P["bn_b"].data_ptr(), m, hid, bn_bits.data_ptr(), st), "rc_debug_bn_relu_mask")
+        MASKS.active.setdefault("layers", []).append({"msg": msg_bits, "bn": bn_bits, "out": bits})
     part, nb = gine_aggr_bwd(d_agg, x, graph, P["lin_w"], P["lin_b"], P["eps"], None if first else dy, dx)
     with on_side(part, d_agg):
         _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, G["lin_w"].data_ptr(), G["lin_b"].data_ptr(),

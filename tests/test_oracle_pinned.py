@@ -171,3 +171,50 @@ def test_model_matches_reference(golden_model, name):
         traj.append(loss.item())
     assert rel_err(np.array(traj), golden_model[f"{name}.adamw.losses"]) < 1e-6
     assert rel_err(model.aggr.weight.detach().numpy(), golden_model[f"{name}.adamw.aggr_weight"]) < 1e-6
+
+
+def test_masked_restatement_matches_oracle_model():
+    """oracle/masked.py (every ReLU as z * mask, the masks optionally forced from outside) is the network of oracle.model.GNN:
+    with its own masks the raw outputs, the CRPS and every gradient agree in float64; forcing those masks back in changes
+    nothing; flipping one message unit's mask changes the gradients (the masks are really in the graph)."""
+    import torch
+    from oracle import masked, model as om, pyg as opyg
+    from oracle.make_golden import model_case_inputs
+    from oracle import graph as og
+    c = model_case_inputs("tiny_mixed_u")
+    ei, ea = og.radius_graph(np.asarray(c["dist"]), c["max_dist"])
+    ei, ea = torch.as_tensor(ei), torch.as_tensor(ea).reshape(-1, 1)
+    b = c["x"].shape[0] // c["n"]
+    data = opyg.Batch.from_data_list([opyg.Data(x=c["x"][i * c["n"]:(i + 1) * c["n"]], ensemble=c["ensemble"][i * c["n"]:(i + 1) * c["n"]],
+                                                y=c["y"][i * c["n"]:(i + 1) * c["n"]], edge_index=ei, edge_attr=ea) for i in range(b)])
+    kw = dict(in_channels=c["f"], hidden_channels_gnn=c["h"], out_channels_gnn=c["h"], num_layers_gnn=c["layers"], loss=c["loss"],
+              grad_u=c["grad_u"], u=1.71, xi=0.5)
+    from raincast_gnn_b200.utils.synthetic import seeded_state_dict
+    ref = om.GNN(**kw)
+    ref.load_state_dict(seeded_state_dict(ref.state_dict(), seed=1234))
+    ref = ref.double()
+    ref.conv.force_float = False
+    ref.train()
+    d64 = opyg.Data(x=data.x.double(), ensemble=data.ensemble.double(), edge_index=data.edge_index, edge_attr=data.edge_attr.double(), y=data.y.double())
+    preds = ref(d64)
+    loss = ref.loss_fn.crps(preds, d64.y)
+    loss.backward()
+    sd = ref.state_dict()
+    args = dict(num_layers=c["layers"], loss=c["loss"], grad_u=c["grad_u"], u=1.71, xi=0.5)
+    p2, l2, g2, used = masked.loss_and_grads(sd, data, **args)
+    assert rel_err(p2.numpy(), preds.detach().numpy()) < 1e-12
+    assert abs(float(l2) - float(loss.detach())) < 1e-12 * abs(float(loss.detach()))
+    named = dict(ref.named_parameters())
+    for k, p in named.items():
+        # (the bias in front of BatchNorm has an exactly-zero true gradient: compared on its weight's scale)
+        scale = named[k[:-4] + "weight"].grad.abs().max().item() if k.endswith(".nn.0.bias") else p.grad.abs().max().item()
+        assert (g2[k] - p.grad).abs().max().item() < 1e-10 * scale, k
+    p3, l3, g3, _ = masked.loss_and_grads(sd, data, masks=used, **args)
+    for k in g2:
+        assert torch.equal(g3[k], g2[k]), k
+    flipped = dict(used)
+    m = used["msg0"].clone()
+    m[0, 0] = ~m[0, 0]
+    flipped["msg0"] = m
+    _, _, g4, _ = masked.loss_and_grads(sd, data, masks=flipped, **args)
+    assert any(not torch.equal(g4[k], g2[k]) for k in g2)
