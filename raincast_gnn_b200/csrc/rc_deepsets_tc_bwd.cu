@@ -39,15 +39,6 @@ struct DsBwdTcP {
   int n_stages;                             // ceil(m / stations per stage)
 };
 
-struct DbSmem {
-  float* raw; int raw_floats;               // ring of kDbRaw raw stages
-  float* a1;                                // W1 tile hi | lo
-  float* b1buf; float* b2buf;               // rings of kDbBuf, hi | lo each
-  int a1_floats, b1_floats, b2_floats;      // floats per hi (or lo) block
-  uint32_t bars;                            // shared address of the barrier block
-  uint32_t* tmem_slot;
-};
-
 // barrier indices (8 bytes each)
 enum { DB_RAW_FULL = 0, DB_RAW_EMPTY = 3, DB_B_FULL = 6, DB_B_EMPTY = 9, DB_D1_FULL = 12, DB_D1_EMPTY = 14, DB_A2_FULL = 16,
        DB_A2_EMPTY = 18, DB_D2_FULL = 20, DB_D2_EMPTY = 22, DB_NBARS = 24 };
@@ -57,7 +48,7 @@ __host__ __device__ inline size_t db_smem_bytes(int feats, int kp, int np) {
   return 128 + 4 * (kDbRaw * raw + 2 * (size_t)128 * kp + kDbBuf * 2 * ((size_t)kDbRows * kp + (size_t)np * kDbRows)) + 8 * DB_NBARS + 16;
 }
 
-template <int MEMBERS>
+template <int MEMBERS, bool DUMP>
 __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(const DsBwdTcP p) {
   pdl_entry();
   constexpr int NPT = kDbRows / MEMBERS;            // stations per stage
@@ -184,6 +175,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
   } else if (warp >= kDbE1Warps) {
     // ================================================================= converters: raw rows -> B1 (E) and B2 (E^T), hi | lo
     const int ct = tid - 32 * kDbE1Warps;                                     // 0..127
+    const float inv_np = 1.0f / (float)NP;
     for (int i = 0; i < n_my; ++i) {
       const int st = blockIdx.x + i * gridDim.x;
       const uint32_t s = i % kDbRaw, ph = (i / kDbRaw) & 1, bb = i % kDbBuf, bph = (i / kDbBuf) & 1;
@@ -222,7 +214,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
       }
       // B2: [NP features][64 rows] K-major over rows; thread <-> (feature, 4-row chunk), consecutive threads = consecutive features
       for (int idx = ct; idx < NP * (kDbRows / 4); idx += 32 * kDbCvtWarps) {
-        const int q = idx / NP, f = idx - q * NP;
+        const int q = __float2int_rd(((float)idx + 0.5f) * inv_np), f = idx - q * NP;     // idx / NP without an integer division
         float v[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -306,7 +298,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
               on = __uint_as_float(r[e]) + bias > 0.f;
               dh = on ? dpv[icol / MEMBERS < NPT ? icol / MEMBERS : 0] : 0.f;
             }
-            if (p.mask_out != nullptr) {
+            if (DUMP) {                                     // (compile-time: the production kernel carries no trace of it)
               const unsigned word = __ballot_sync(0xffffffffu, on && cok);
               const long long row = (long long)n0 * MEMBERS + icol;
               if (lane == 0 && icol < USED && row < (long long)p.m * MEMBERS && c0 + quarter * 32 < p.hidden)
@@ -392,17 +384,20 @@ int launch_deepsets_bwd_tc(const float* ens, const float* w1, const float* b1, c
   if (smem > 227 * 1024) return fail(RC_ERR_ARG, "deepsets tensor-core backward: feats=%d needs %zu bytes of shared memory", feats, smem);
   if (!aligned16(ens)) return fail(RC_ERR_ARG, "deepsets tensor-core backward: ens must be 16-byte aligned");
   dim3 grid(deepsets_bwd_tc_blocks(num_nodes, members), ceil_div(hidden, 128));
-  cudaError_t e = cudaSuccess;
-  static size_t attr11 = 0, attr51 = 0;
-  if (members == 11) {
-    if (smem > attr11) { e = cudaFuncSetAttribute(deepsets_pool_bwd_tc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr11 = smem; }
-    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core backward: %s", cudaGetErrorString(e));
-    launch_pdl(deepsets_pool_bwd_tc_kernel<11>, grid, dim3(kDbThreads), smem, s, p);
-  } else {
-    if (smem > attr51) { e = cudaFuncSetAttribute(deepsets_pool_bwd_tc_kernel<51>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr51 = smem; }
-    if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core backward: %s", cudaGetErrorString(e));
-    launch_pdl(deepsets_pool_bwd_tc_kernel<51>, grid, dim3(kDbThreads), smem, s, p);
-  }
+  auto go = [&](auto kern, size_t& attr) -> int {
+    if (smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(RC_ERR_CUDA, "deepsets tensor-core backward: %s", cudaGetErrorString(e));
+      attr = smem;
+    }
+    launch_pdl(kern, grid, dim3(kDbThreads), smem, s, p);
+    return RC_OK;
+  };
+  static size_t attr[4] = {0, 0, 0, 0};
+  int rc;
+  if (members == 11) rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<11, true>, attr[0]) : go(deepsets_pool_bwd_tc_kernel<11, false>, attr[1]);
+  else rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<51, true>, attr[2]) : go(deepsets_pool_bwd_tc_kernel<51, false>, attr[3]);
+  if (rc) return rc;
   return check_launch("deepsets_pool_bwd_tc_kernel");
 }
 

@@ -620,6 +620,9 @@ struct TcWgradP {
   int mblocks, per_split;        // 32-sample blocks in total / per reduction split
 };
 
+// OPA / OPB: the operand prologues as compile-time constants for the combinations a training step uses (-1: read them
+// from the descriptor at run time)
+template <int OPA, int OPB>
 __global__ void __launch_bounds__(kTcWgThreads, 1) gemm_tc_wgrad_kernel(const TcWgradP p) {
   pdl_entry();
   extern __shared__ unsigned char smem_raw[];
@@ -657,12 +660,13 @@ __global__ void __launch_bounds__(kTcWgThreads, 1) gemm_tc_wgrad_kernel(const Tc
     const int ia = i0 + il, jb = j0 + il;
     const bool a_ok = ia < g.m, b_ok = jb < g.n;
     float colsum = 0.f;
+    const int opa = OPA >= 0 ? OPA : g.a.op, opb = OPB >= 0 ? OPB : g.b.op;
     // the operand prologues' per-column vectors: this thread's column never changes
     float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a_ok && (g.a.op == RC_OP_BN_RELU || g.a.op == RC_OP_AFFINE2)) {
+    if (a_ok && (opa == RC_OP_BN_RELU || opa == RC_OP_AFFINE2)) {
       pa[0] = __ldg(g.a.p0 + ia); pa[1] = __ldg(g.a.p1 + ia); pa[2] = __ldg(g.a.p2 + ia); pa[3] = __ldg(g.a.p3 + ia);
     }
-    if (b_ok && (g.b.op == RC_OP_BN_RELU || g.b.op == RC_OP_AFFINE2)) {
+    if (b_ok && (opb == RC_OP_BN_RELU || opb == RC_OP_AFFINE2)) {
       pb[0] = __ldg(g.b.p0 + jb); pb[1] = __ldg(g.b.p1 + jb); pb[2] = __ldg(g.b.p2 + jb); pb[3] = __ldg(g.b.p3 + jb);
     }
     // stored element -> operand value (same arithmetic as apply_op in rc_gemm_tile.cuh)
@@ -689,15 +693,15 @@ __global__ void __launch_bounds__(kTcWgThreads, 1) gemm_tc_wgrad_kernel(const Tc
           const bool ra = a_ok && r + e < g.k, rb = b_ok && r + e < g.k;
           t[e] = ra ? __ldg(g.a.ptr + (size_t)(r + e) * g.a.ld + ia) : 0.f;
           u[e] = rb ? __ldg(g.b.ptr + (size_t)(r + e) * g.b.ld + jb) : 0.f;
-          if (g.a.op == RC_OP_AFFINE2 && ra) xa[e] = __ldg(g.a.aux + (size_t)(r + e) * g.a.ld_aux + ia);
-          if (g.b.op == RC_OP_AFFINE2 && rb) xb[e] = __ldg(g.b.aux + (size_t)(r + e) * g.b.ld_aux + jb);
-          if (g.a.op == RC_OP_BITMASK && ra) wa[e] = __ldg(g.a.bits + (size_t)(r + e) * g.a.ld_bits + (ia >> 5));
-          if (g.b.op == RC_OP_BITMASK && rb) wb[e] = __ldg(g.b.bits + (size_t)(r + e) * g.b.ld_bits + (jb >> 5));
+          if (opa == RC_OP_AFFINE2 && ra) xa[e] = __ldg(g.a.aux + (size_t)(r + e) * g.a.ld_aux + ia);
+          if (opb == RC_OP_AFFINE2 && rb) xb[e] = __ldg(g.b.aux + (size_t)(r + e) * g.b.ld_aux + jb);
+          if (opa == RC_OP_BITMASK && ra) wa[e] = __ldg(g.a.bits + (size_t)(r + e) * g.a.ld_bits + (ia >> 5));
+          if (opb == RC_OP_BITMASK && rb) wb[e] = __ldg(g.b.bits + (size_t)(r + e) * g.b.ld_bits + (jb >> 5));
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (g.a.op != RC_OP_NONE && a_ok && r + e < g.k) t[e] = prologue(g.a.op, t[e], xa[e], wa[e], ia, pa);
-          if (g.b.op != RC_OP_NONE && b_ok && r + e < g.k) u[e] = prologue(g.b.op, u[e], xb[e], wb[e], jb, pb);
+          if (opa != RC_OP_NONE && a_ok && r + e < g.k) t[e] = prologue(opa, t[e], xa[e], wa[e], ia, pa);
+          if (opb != RC_OP_NONE && b_ok && r + e < g.k) u[e] = prologue(opb, u[e], xb[e], wb[e], jb, pb);
         }
         va[q] = make_float4(t[0], t[1], t[2], t[3]);
         vb[q] = make_float4(u[0], u[1], u[2], u[3]);
@@ -851,7 +855,10 @@ int gemm_tc_run(const rc_gemm* g, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_wgrad_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_tc_wgrad_kernel<RC_OP_NONE, RC_OP_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_tc_wgrad_kernel<RC_OP_AFFINE2, RC_OP_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_tc_wgrad_kernel<RC_OP_BITMASK, RC_OP_BN_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     cudaError_t e3 = cudaFuncSetAttribute(gemm_tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     if (e1 == cudaSuccess) e1 = e3;
     if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(RC_ERR_CUDA, "rc_gemm_run (tensor cores): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -905,7 +912,15 @@ int gemm_tc_run(const rc_gemm* g, cudaStream_t s) {
     p.mblocks = ceil_div(g->k, 32);
     const int splits = g->splits > 1 ? g->splits : 1;
     p.per_split = ceil_div(p.mblocks, splits);
-    launch_pdl(gemm_tc_wgrad_kernel, dim3(splits, p.i_tiles * p.j_tiles), dim3(kTcWgThreads), (size_t)kTcSmemBytes, s, p);
+    const dim3 wgrid(splits, p.i_tiles * p.j_tiles);
+    if (g->a.op == RC_OP_NONE && g->b.op == RC_OP_NONE)
+      launch_pdl(gemm_tc_wgrad_kernel<RC_OP_NONE, RC_OP_NONE>, wgrid, dim3(kTcWgThreads), (size_t)kTcSmemBytes, s, p);
+    else if (g->a.op == RC_OP_AFFINE2 && g->b.op == RC_OP_NONE)
+      launch_pdl(gemm_tc_wgrad_kernel<RC_OP_AFFINE2, RC_OP_NONE>, wgrid, dim3(kTcWgThreads), (size_t)kTcSmemBytes, s, p);
+    else if (g->a.op == RC_OP_BITMASK && g->b.op == RC_OP_BN_RELU)
+      launch_pdl(gemm_tc_wgrad_kernel<RC_OP_BITMASK, RC_OP_BN_RELU>, wgrid, dim3(kTcWgThreads), (size_t)kTcSmemBytes, s, p);
+    else
+      launch_pdl(gemm_tc_wgrad_kernel<-1, -1>, wgrid, dim3(kTcWgThreads), (size_t)kTcSmemBytes, s, p);
     return check_launch("gemm_tc_wgrad_kernel");
   }
   return fail(RC_ERR_ARG, "rc_gemm_run: tensor-core path not applicable");
