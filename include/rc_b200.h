@@ -341,6 +341,8 @@ int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, const float
                           int m, int n, uint32_t* bits_out, void* stream);
 /* tensor-core GEMM timeline of CTA 0 (tools/trace_gemm_tc.py) */
 void rc_debug_tc_trace(void* device_buf);
+/* tensor-core DeepSets pool backward: clocks of CTA 0, int64 [8 events][32 stages] (tools/trace_pool_bwd.py) */
+void rc_debug_ds_trace(void* device_buf);
 
 #ifdef __cplusplus
 }

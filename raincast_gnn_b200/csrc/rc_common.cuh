@@ -94,6 +94,7 @@ int launch_deepsets_fwd_tc(bool bf16, const float* ens, const float* w1, const f
 // rc_deepsets_tc_bwd.cu: tcgen05 / TMEM path of the DeepSets pool backward (members 11 / 51)
 bool deepsets_bwd_tc_applicable(int num_nodes, int members, int feats, int hidden);
 int deepsets_bwd_tc_blocks(int num_nodes, int members);
+void deepsets_bwd_tc_set_trace(long long* p);
 int launch_deepsets_bwd_tc(const float* ens, const float* w1, const float* b1, const float* d_pooled, float* partials,
                            uint32_t* mask_out, int num_nodes, int members, int feats, int hidden, int bf16, cudaStream_t s);
 

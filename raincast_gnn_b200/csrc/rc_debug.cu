@@ -86,3 +86,5 @@ extern "C" int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, 
   dbg_bn_relu_mask_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, ld, mean, rstd, gamma, beta, m, n, bits_out);
   return check_launch("dbg_bn_relu_mask_kernel");
 }
+
+extern "C" void rc_debug_ds_trace(void* device_buf) { deepsets_bwd_tc_set_trace(static_cast<long long*>(device_buf)); }

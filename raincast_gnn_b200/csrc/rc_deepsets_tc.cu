@@ -45,6 +45,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a, uint64_t 
                :: "r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate));
 }
 
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
@@ -232,20 +238,23 @@ deepsets_pool_fwd_tc_kernel(const float* __restrict__ ens, const float* __restri
     if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     for (int y = 0; y < ny; ++y) {
       // ---- one thread issues the MMAs of this hidden chunk; completion arrives on the mbarrier
-      if (tid == 0) {
+      if (warp == 0) {                                    // converged here (just past the barrier): one elected lane issues
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t ah = smem_u32(smem_raw) + y * a_bytes, al = ah + op_bytes, bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = ks * 2 * kTcChunkBytes;
-          if (BF16) {
-            umma_bf16(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
-          } else {
-            umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
-            umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bl + off), idesc, 1);
-            umma_tf32(tmem_base, umma_desc(al + off), umma_desc(bh + off), idesc, 1);
+        if (tc_elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t off = ks * 2 * kTcChunkBytes;
+            if (BF16) {
+              umma_bf16(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
+            } else {
+              umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bh + off), idesc, ks > 0);
+              umma_tf32(tmem_base, umma_desc(ah + off), umma_desc(bl + off), idesc, 1);
+              umma_tf32(tmem_base, umma_desc(al + off), umma_desc(bh + off), idesc, 1);
+            }
           }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
+        __syncwarp();
       }
       mbar_wait(smem_u32(mbar), phase);
       phase ^= 1;

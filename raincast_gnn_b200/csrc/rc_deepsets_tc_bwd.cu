@@ -37,7 +37,11 @@ struct DsBwdTcP {
   int kp, np;                               // feats padded to 8 (MMA1 K) / to 16 (MMA2 N)
   int bf16;                                 // operands rounded to bf16 first (the forward ran on bf16 tensor cores)
   int n_stages;                             // ceil(m / stations per stage)
+  long long* trace;                         // debug (rc_debug_ds_trace): CTA 0, [event 0..7][stage < 32] clock
 };
+__device__ __forceinline__ void db_trace(long long* trace, int ev, int i) {
+  if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && i < 32 && (threadIdx.x & 31) == 0) trace[ev * 32 + i] = clock64();
+}
 
 // barrier indices (8 bytes each)
 enum { DB_RAW_FULL = 0, DB_RAW_EMPTY = 3, DB_B_FULL = 6, DB_B_EMPTY = 9, DB_D1_FULL = 12, DB_D1_EMPTY = 14, DB_A2_FULL = 16,
@@ -48,7 +52,8 @@ __host__ __device__ inline size_t db_smem_bytes(int feats, int kp, int np) {
   return 128 + 4 * (kDbRaw * raw + 2 * (size_t)128 * kp + kDbBuf * 2 * ((size_t)kDbRows * kp + (size_t)np * kDbRows)) + 8 * DB_NBARS + 16;
 }
 
-template <int MEMBERS, bool DUMP>
+// FIXED: 33..40 features (the reference has 35): KP = 40, NP = 48 are compile-time and the converter loops unroll
+template <int MEMBERS, bool DUMP, bool FIXED>
 __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(const DsBwdTcP p) {
   pdl_entry();
   constexpr int NPT = kDbRows / MEMBERS;            // stations per stage
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
   constexpr int KS2 = (USED + 7) / 8;               // MMA2 k-steps
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
-  const int F = p.feats, KP = p.kp, NP = p.np;
+  const int F = p.feats, KP = FIXED ? 40 : p.kp, NP = FIXED ? 48 : p.np;
   const int raw_floats = (kDbRows * F + 8 + 3) / 4 * 4;
   float* raw = reinterpret_cast<float*>(base);
   float* a1 = raw + kDbRaw * raw_floats;
@@ -126,52 +131,62 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
       }
     }
   } else if (warp == kDbE1Warps + kDbCvtWarps) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc(2u, kDbRows), idesc2 = umma_idesc(2u, NP);
-      const uint32_t lbo = 128, sbo1a = (uint32_t)(KP / 4) * 128, sbo2 = (kDbRows / 4) * 128;
-      const int ks1 = KP / 8;
-      auto mma2 = [&](int i) {                                              // D2 += dh(stage i) . E(stage i)
-        const uint32_t ab = i & 1, aph = (i >> 1) & 1, bb = i % kDbBuf;
-        const uint32_t pair = (i >> 1) & 1, pph = (i >> 2) & 1;
-        mbar_wait(bar(DB_A2_FULL + ab), aph);
-        if ((i & 1) == 0) mbar_wait(bar(DB_D2_EMPTY + pair), pph ^ 1);       // first stage of a pair: the accumulator was flushed
-        tc_fence_after();
-        const uint32_t a_hi = t_a2 + ab * 128, a_lo = a_hi + 64, d2 = t_d2 + pair * 64;
-        const uint32_t bh = smem_u32(b2buf + bb * 2 * b2_floats), bl = bh + b2_floats * 4;
+    // ================================================================= MMA issuer (the whole warp waits, one elected lane issues)
+    const uint32_t idesc1 = umma_idesc(2u, kDbRows), idesc2 = umma_idesc(2u, NP);
+    const uint32_t lbo = 128, sbo1a = (uint32_t)(KP / 4) * 128, sbo2 = (kDbRows / 4) * 128;
+    const int ks1 = KP / 8;
+    const UmmaDesc a1h = umma_desc2(smem_u32(a1), lbo, sbo1a);
+    const uint32_t a1_lo_off = a1_floats * 4;
+    auto mma2 = [&](int i) {                                                // D2 += dh(stage i) . E(stage i)
+      const uint32_t ab = i & 1, aph = (i >> 1) & 1, bb = i % kDbBuf;
+      const uint32_t pair = (i >> 1) & 1, pph = (i >> 2) & 1;
+      mbar_wait(bar(DB_A2_FULL + ab), aph);
+      if ((i & 1) == 0) mbar_wait(bar(DB_D2_EMPTY + pair), pph ^ 1);         // first stage of a pair: the accumulator was flushed
+      tc_fence_after();
+      if (lane == 0) db_trace(p.trace, 3, i);
+      const uint32_t a_hi = t_a2 + ab * 128, a_lo = a_hi + 64, d2 = t_d2 + pair * 64;
+      const UmmaDesc bh = umma_desc2(smem_u32(b2buf + bb * 2 * b2_floats), lbo, sbo2);
+      const uint32_t b_lo_off = b2_floats * 4;
+      if (elect_one()) {
+#pragma unroll
         for (int ks = 0; ks < KS2; ++ks) {
           const uint32_t off = ks * 2 * lbo;
-          umma_tf32_ts(d2, a_lo + ks * 8, umma_desc(bh + off, lbo, sbo2), idesc2, ((i & 1) == 0 && ks == 0) ? 0u : 1u);
-          if (!p.bf16) umma_tf32_ts(d2, a_hi + ks * 8, umma_desc(bl + off, lbo, sbo2), idesc2, 1u);
-          umma_tf32_ts(d2, a_hi + ks * 8, umma_desc(bh + off, lbo, sbo2), idesc2, 1u);
+          umma_tf32_ts(d2, a_lo + ks * 8, bh.at(off), idesc2, ((i & 1) == 0 && ks == 0) ? 0u : 1u);
+          if (!p.bf16) umma_tf32_ts(d2, a_hi + ks * 8, bh.at(b_lo_off + off), idesc2, 1u);
+          umma_tf32_ts(d2, a_hi + ks * 8, bh.at(off), idesc2, 1u);
         }
         umma_commit(bar(DB_B_EMPTY + bb));
         umma_commit(bar(DB_A2_EMPTY + ab));
         if ((i & 1) == 1 || i == n_my - 1) umma_commit(bar(DB_D2_FULL + pair));
-      };
-      for (int i = 0; i < n_my; ++i) {
-        const uint32_t db = i & 1, dph = (i >> 1) & 1, bb = i % kDbBuf, bph = (i / kDbBuf) & 1;
-        mbar_wait(bar(DB_B_FULL + bb), bph);
-        mbar_wait(bar(DB_D1_EMPTY + db), dph ^ 1);
-        tc_fence_after();
-        const uint32_t ah = smem_u32(a1), al = ah + a1_floats * 4;
-        const uint32_t bh = smem_u32(b1buf + bb * 2 * b1_floats), bl = bh + b1_floats * 4;
-        const uint32_t d1 = t_d1 + db * 64;
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < n_my; ++i) {
+      const uint32_t db = i & 1, dph = (i >> 1) & 1, bb = i % kDbBuf, bph = (i / kDbBuf) & 1;
+      mbar_wait(bar(DB_B_FULL + bb), bph);
+      mbar_wait(bar(DB_D1_EMPTY + db), dph ^ 1);
+      tc_fence_after();
+      if (lane == 0) db_trace(p.trace, 2, i);
+      const UmmaDesc bh = umma_desc2(smem_u32(b1buf + bb * 2 * b1_floats), lbo, sbo1a);
+      const uint32_t b_lo_off = b1_floats * 4;
+      const uint32_t d1 = t_d1 + db * 64;
+      if (elect_one()) {
         for (int ks = 0; ks < ks1; ++ks) {
           const uint32_t off = ks * 2 * lbo;
           if (!p.bf16) {
-            umma_tf32(d1, umma_desc(al + off, lbo, sbo1a), umma_desc(bh + off, lbo, sbo1a), idesc1, ks == 0 ? 0u : 1u);
-            umma_tf32(d1, umma_desc(ah + off, lbo, sbo1a), umma_desc(bl + off, lbo, sbo1a), idesc1, 1u);
-            umma_tf32(d1, umma_desc(ah + off, lbo, sbo1a), umma_desc(bh + off, lbo, sbo1a), idesc1, 1u);
+            umma_tf32(d1, a1h.at(a1_lo_off + off), bh.at(off), idesc1, ks == 0 ? 0u : 1u);
+            umma_tf32(d1, a1h.at(off), bh.at(b_lo_off + off), idesc1, 1u);
+            umma_tf32(d1, a1h.at(off), bh.at(off), idesc1, 1u);
           } else {
-            umma_tf32(d1, umma_desc(ah + off, lbo, sbo1a), umma_desc(bh + off, lbo, sbo1a), idesc1, ks == 0 ? 0u : 1u);
+            umma_tf32(d1, a1h.at(off), bh.at(off), idesc1, ks == 0 ? 0u : 1u);
           }
         }
         umma_commit(bar(DB_D1_FULL + db));
-        if (i >= 1) mma2(i - 1);
       }
-      if (n_my >= 1) mma2(n_my - 1);
+      __syncwarp();
+      if (i >= 1) mma2(i - 1);
     }
+    if (n_my >= 1) mma2(n_my - 1);
   } else if (warp >= kDbE1Warps) {
     // ================================================================= converters: raw rows -> B1 (E) and B2 (E^T), hi | lo
     const int ct = tid - 32 * kDbE1Warps;                                     // 0..127
@@ -193,9 +208,52 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
         }
       }
       mbar_wait(bar(DB_B_EMPTY + bb), bph ^ 1);
+      if (ct == 0) db_trace(p.trace, 0, i);
       const float* e = rw + mis;
       float* b1h = b1buf + bb * 2 * b1_floats, *b1l = b1h + b1_floats;
       float* b2h = b2buf + bb * 2 * b2_floats, *b2l = b2h + b2_floats;
+      auto round_op = [&](float v) { return p.bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : v; };
+      if constexpr (FIXED) {
+        // every shared-memory read of the stage is issued before the first conversion (one converter warp per
+        // sub-partition: without instruction-level parallelism the role is bound by the 29-cycle LDS latency)
+        constexpr int N1 = kDbRows * (40 / 4) / (32 * kDbCvtWarps);           // 5 chunks of B1 per thread
+        constexpr int N2 = 48 * (kDbRows / 4) / (32 * kDbCvtWarps);           // 6 chunks of B2 per thread
+        float v1[N1][4], v2[N2][4];
+#pragma unroll
+        for (int it = 0; it < N1; ++it) {
+          const int idx = ct + it * 32 * kDbCvtWarps;
+          const int q = idx >> 6, r = idx & 63;                               // (4-feature chunk, row): consecutive threads = consecutive rows
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v1[it][t] = (r < rows && 4 * q + t < F) ? e[r * F + 4 * q + t] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < N2; ++it) {
+          const int idx = ct + it * 32 * kDbCvtWarps;
+          const int q = idx / 48, f = idx - q * 48;                           // (4-row chunk, feature): consecutive threads = consecutive features
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v2[it][t] = (4 * q + t < rows && f < F) ? e[(4 * q + t) * F + f] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < N1; ++it) {
+          const int idx = ct + it * 32 * kDbCvtWarps;
+          const int q = idx >> 6, r = idx & 63;
+          float4 hi, lo;
+          split_tf32_trunc(make_float4(round_op(v1[it][0]), round_op(v1[it][1]), round_op(v1[it][2]), round_op(v1[it][3])), hi, lo);
+          const int o = (r >> 3) * (40 / 4) * 32 + q * 32 + (r & 7) * 4;
+          st4(b1h + o, hi);
+          st4(b1l + o, lo);
+        }
+#pragma unroll
+        for (int it = 0; it < N2; ++it) {
+          const int idx = ct + it * 32 * kDbCvtWarps;
+          const int q = idx / 48, f = idx - q * 48;
+          float4 hi, lo;
+          split_tf32_trunc(make_float4(round_op(v2[it][0]), round_op(v2[it][1]), round_op(v2[it][2]), round_op(v2[it][3])), hi, lo);
+          const int o = (f >> 3) * (kDbRows / 4) * 32 + q * 32 + (f & 7) * 4;
+          st4(b2h + o, hi);
+          st4(b2l + o, lo);
+        }
+      } else {
       // B1: [64 rows][KP] K-major over features; thread <-> (row, 4-feature chunk), consecutive threads = consecutive rows
       for (int idx = ct; idx < kDbRows * (KP / 4); idx += 32 * kDbCvtWarps) {
         const int q = idx / kDbRows, r = idx - q * kDbRows;
@@ -203,11 +261,10 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int k = 4 * q + t;
-          v[t] = (r < rows && k < F) ? e[r * F + k] : 0.f;
-          if (p.bf16) v[t] = __bfloat162float(__float2bfloat16_rn(v[t]));
+          v[t] = round_op((r < rows && k < F) ? e[r * F + k] : 0.f);
         }
         float4 hi, lo;
-        split_tf32(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+        split_tf32_trunc(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
         const int o = (r >> 3) * (KP / 4) * 32 + q * 32 + (r & 7) * 4;
         st4(b1h + o, hi);
         st4(b1l + o, lo);
@@ -219,14 +276,14 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int r = 4 * q + t;
-          v[t] = (r < rows && f < F) ? e[r * F + f] : 0.f;
-          if (p.bf16) v[t] = __bfloat162float(__float2bfloat16_rn(v[t]));
+          v[t] = round_op((r < rows && f < F) ? e[r * F + f] : 0.f);
         }
         float4 hi, lo;
-        split_tf32(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+        split_tf32_trunc(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
         const int o = (f >> 3) * (kDbRows / 4) * 32 + q * 32 + (f & 7) * 4;
         st4(b2h + o, hi);
         st4(b2l + o, lo);
+      }
       }
       fence_async_smem();
       __syncwarp();
@@ -234,6 +291,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
         mbar_arrive(bar(DB_B_FULL + bb));
         mbar_arrive(bar(DB_RAW_EMPTY + s));
       }
+      if (ct == 0) db_trace(p.trace, 1, i);
     }
   } else {
     // ================================================================= E1: thread = channel (TMEM lane), 32 of the stage's columns
@@ -279,6 +337,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
       mbar_wait(bar(DB_D1_FULL + db), dph);
       mbar_wait(bar(DB_A2_EMPTY + db), dph ^ 1);
       tc_fence_after();
+      if (warp == 0) db_trace(p.trace, 4, i);
       const uint32_t td = t_d1 + db * 64 + half * 32 + lane_base;
       const uint32_t ta = t_a2 + db * 128 + half * 32 + lane_base;
       auto e1_body = [&](auto half_c) {                   // `half` as a compile-time constant: the column -> station map is static
@@ -322,7 +381,9 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
         mbar_arrive(bar(DB_D1_EMPTY + db));
         mbar_arrive(bar(DB_A2_FULL + db));
       }
+      if (warp == 0) db_trace(p.trace, 5, i);
       if (i >= 2 && (i & 1) == 0) flush((i >> 1) - 1);  // the pair that ended two stages ago has long completed
+      if (warp == 0) db_trace(p.trace, 6, i);
     }
     // remaining pairs: (n_my + 1) / 2 pairs in total
     {
@@ -352,6 +413,9 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static long long* g_ds_trace = nullptr;
+void deepsets_bwd_tc_set_trace(long long* p) { g_ds_trace = p; }
+
 bool deepsets_bwd_tc_applicable(int num_nodes, int members, int feats, int hidden) {
   static int forced = -1;
   if (forced < 0) {
@@ -380,6 +444,7 @@ int launch_deepsets_bwd_tc(const float* ens, const float* w1, const float* b1, c
   p.bf16 = bf16;
   const int npt = kDbRows / members;
   p.n_stages = ceil_div(num_nodes, npt);
+  p.trace = g_ds_trace;
   const size_t smem = db_smem_bytes(feats, p.kp, p.np);
   if (smem > 227 * 1024) return fail(RC_ERR_ARG, "deepsets tensor-core backward: feats=%d needs %zu bytes of shared memory", feats, smem);
   if (!aligned16(ens)) return fail(RC_ERR_ARG, "deepsets tensor-core backward: ens must be 16-byte aligned");
@@ -393,10 +458,16 @@ int launch_deepsets_bwd_tc(const float* ens, const float* w1, const float* b1, c
     launch_pdl(kern, grid, dim3(kDbThreads), smem, s, p);
     return RC_OK;
   };
-  static size_t attr[4] = {0, 0, 0, 0};
+  static size_t attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool fixed = p.kp == 40 && p.np == 48;
   int rc;
-  if (members == 11) rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<11, true>, attr[0]) : go(deepsets_pool_bwd_tc_kernel<11, false>, attr[1]);
-  else rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<51, true>, attr[2]) : go(deepsets_pool_bwd_tc_kernel<51, false>, attr[3]);
+  if (members == 11) {
+    if (fixed) rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<11, true, true>, attr[0]) : go(deepsets_pool_bwd_tc_kernel<11, false, true>, attr[1]);
+    else rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<11, true, false>, attr[2]) : go(deepsets_pool_bwd_tc_kernel<11, false, false>, attr[3]);
+  } else {
+    if (fixed) rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<51, true, true>, attr[4]) : go(deepsets_pool_bwd_tc_kernel<51, false, true>, attr[5]);
+    else rc = mask_out ? go(deepsets_pool_bwd_tc_kernel<51, true, false>, attr[6]) : go(deepsets_pool_bwd_tc_kernel<51, false, false>, attr[7]);
+  }
   if (rc) return rc;
   return check_launch("deepsets_pool_bwd_tc_kernel");
 }

@@ -112,26 +112,26 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* raw) {
 
 // 12 MMAs of one stage: 4 k-steps of 8, three TF32 products each
 __device__ __forceinline__ void tc_issue_stage(uint32_t stage_addr, uint32_t tmem_d, uint32_t idesc, bool first) {
-  const uint32_t ah = stage_addr, al = ah + kTcBlkBytes, bh = al + kTcBlkBytes, bl = bh + kTcBlkBytes;
+  const UmmaDesc ah = umma_desc2(stage_addr, kTcLBO, kTcSBO);           // A hi; A lo, B hi, B lo follow at 16 KB steps
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     const uint32_t off = ks * 2 * kTcLBO;
-    umma_tf32(tmem_d, umma_desc(al + off, kTcLBO, kTcSBO), umma_desc(bh + off, kTcLBO, kTcSBO), idesc, (first && ks == 0) ? 0u : 1u);
-    umma_tf32(tmem_d, umma_desc(ah + off, kTcLBO, kTcSBO), umma_desc(bl + off, kTcLBO, kTcSBO), idesc, 1u);
-    umma_tf32(tmem_d, umma_desc(ah + off, kTcLBO, kTcSBO), umma_desc(bh + off, kTcLBO, kTcSBO), idesc, 1u);
+    umma_tf32(tmem_d, ah.at(kTcBlkBytes + off), ah.at(2 * kTcBlkBytes + off), idesc, (first && ks == 0) ? 0u : 1u);
+    umma_tf32(tmem_d, ah.at(off), ah.at(3 * kTcBlkBytes + off), idesc, 1u);
+    umma_tf32(tmem_d, ah.at(off), ah.at(2 * kTcBlkBytes + off), idesc, 1u);
   }
 }
 
 // the same with the A operand (the weight tile, hi at a_tmem, lo 128 columns further) read from TMEM: the tensor core
 // fetches only B from shared memory, which halves the shared-memory traffic of a stage
 __device__ __forceinline__ void tc_issue_stage_atm(uint32_t b_addr, uint32_t a_tmem, uint32_t tmem_d, uint32_t idesc, bool first) {
-  const uint32_t bh = b_addr, bl = bh + kTcBlkBytes;
+  const UmmaDesc bh = umma_desc2(b_addr, kTcLBO, kTcSBO);               // B hi; B lo follows 16 KB later
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
     const uint32_t off = ks * 2 * kTcLBO;
-    umma_tf32_ts(tmem_d, a_tmem + 128 + ks * 8, umma_desc(bh + off, kTcLBO, kTcSBO), idesc, (first && ks == 0) ? 0u : 1u);
-    umma_tf32_ts(tmem_d, a_tmem + ks * 8, umma_desc(bl + off, kTcLBO, kTcSBO), idesc, 1u);
-    umma_tf32_ts(tmem_d, a_tmem + ks * 8, umma_desc(bh + off, kTcLBO, kTcSBO), idesc, 1u);
+    umma_tf32_ts(tmem_d, a_tmem + 128 + ks * 8, bh.at(off), idesc, (first && ks == 0) ? 0u : 1u);
+    umma_tf32_ts(tmem_d, a_tmem + ks * 8, bh.at(kTcBlkBytes + off), idesc, 1u);
+    umma_tf32_ts(tmem_d, a_tmem + ks * 8, bh.at(off), idesc, 1u);
   }
 }
 
@@ -477,32 +477,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_rows_kernel(const TcRow
       default: tc_rows_producer<RC_OP_NONE, ATM>(p, sm, pw, lane, n_tiles_total); break;
     }
   } else if (warp == kTcEpiWarps + kTcRowsProdWarps) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(2u, 128);
-      uint32_t cnt = 0, tcount = 0;
-      if (ATM) {
-        mbar_wait(sm.w_ready, 0);                          // the weight tile is in TMEM
+    // ================================================================= MMA issuer (the whole warp waits, one elected lane issues)
+    const uint32_t idesc = umma_idesc(2u, 128);
+    uint32_t cnt = 0, tcount = 0;
+    if (ATM) {
+      mbar_wait(sm.w_ready, 0);                            // the weight tile is in TMEM
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount % nbuf, aph = (tcount / nbuf) & 1;
+      mbar_wait(sm.tmem_empty + 8 * acc, aph ^ 1);
+      tc_fence_after();
+      if (lane == 0) tc_trace(p.trace, 1, tcount, 0);
+      for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
+        const uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1;
+        const uint32_t tmem_d = tmem_base + (acc * groups + kb / kTcChain) * 128;
+        mbar_wait(sm.full + 8 * s, ph);
         tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount % nbuf, aph = (tcount / nbuf) & 1;
-        mbar_wait(sm.tmem_empty + 8 * acc, aph ^ 1);
-        tc_fence_after();
-        tc_trace(p.trace, 1, tcount, 0);
-        for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
-          const uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1;
-          const uint32_t tmem_d = tmem_base + (acc * groups + kb / kTcChain) * 128;
-          mbar_wait(sm.full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t st = smem_u32(sm.stages + (size_t)s * kStageBytes);
+        const uint32_t st = smem_u32(sm.stages + (size_t)s * kStageBytes);
+        if (elect_one()) {
           if (ATM) tc_issue_stage_atm(st, w_tmem + kb * 32, tmem_d, idesc, kb % kTcChain == 0);
           else tc_issue_stage(st, tmem_d, idesc, kb % kTcChain == 0);
           umma_commit(sm.empty + 8 * s);
+          if (kb == p.kblocks - 1) umma_commit(sm.tmem_full + 8 * acc);
         }
-        umma_commit(sm.tmem_full + 8 * acc);
-        tc_trace(p.trace, 1, tcount, 1);
+        __syncwarp();
       }
+      if (lane == 0) tc_trace(p.trace, 1, tcount, 1);
     }
   } else {
     // ================================================================= epilogue: thread = output channel
@@ -733,22 +734,23 @@ __global__ void __launch_bounds__(kTcWgThreads, 1) gemm_tc_wgrad_kernel(const Tc
       if (pw < 4 && a_ok) g.colsum_a[(size_t)z * g.m + ia] = cs_smem[il] + cs_smem[128 + il];
     }
   } else if (warp == kTcWgEpiWarps + kTcProdWarps) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(2u, 128);
-      uint32_t cnt = 0;
-      for (int gi = 0; gi < n_groups; ++gi) {
-        const uint32_t acc = gi & 1, aph = (gi >> 1) & 1;
-        mbar_wait(sm.tmem_empty + 8 * acc, aph ^ 1);
+    const uint32_t idesc = umma_idesc(2u, 128);
+    uint32_t cnt = 0;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const uint32_t acc = gi & 1, aph = (gi >> 1) & 1;
+      mbar_wait(sm.tmem_empty + 8 * acc, aph ^ 1);
+      tc_fence_after();
+      const int g_beg = mb_beg + gi * kTcChain, g_end = min(mb_end, g_beg + kTcChain);
+      for (int mb = g_beg; mb < g_end; ++mb, ++cnt) {
+        const uint32_t s = cnt % kTcStages, ph = (cnt / kTcStages) & 1;
+        mbar_wait(sm.full + 8 * s, ph);
         tc_fence_after();
-        const int g_beg = mb_beg + gi * kTcChain, g_end = min(mb_end, g_beg + kTcChain);
-        for (int mb = g_beg; mb < g_end; ++mb, ++cnt) {
-          const uint32_t s = cnt % kTcStages, ph = (cnt / kTcStages) & 1;
-          mbar_wait(sm.full + 8 * s, ph);
-          tc_fence_after();
+        if (elect_one()) {
           tc_issue_stage(smem_u32(sm.stages + (size_t)s * kTcStageBytes), tmem_base + acc * 128, idesc, mb == g_beg);
           umma_commit(sm.empty + 8 * s);
+          if (mb == g_end - 1) umma_commit(sm.tmem_full + 8 * acc);
         }
-        umma_commit(sm.tmem_full + 8 * acc);
+        __syncwarp();
       }
     }
   } else {

@@ -17,6 +17,27 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
          (1ull << 46);
 }
 
+// The same descriptor as two 32-bit halves, so that stepping through an operand is ONE 32-bit add on the low word.
+// (The thread that issues the MMAs is a single instruction stream: with ~16 instructions of descriptor arithmetic per
+//  tcgen05.mma it issued one MMA per ~90 cycles - slower than the tensor core executes a 128 x 128 x 8 TF32 MMA.)
+struct UmmaDesc {
+  uint32_t lo, hi;
+  __device__ __forceinline__ uint64_t at(uint32_t byte_off) const { return ((uint64_t)hi << 32) | (uint64_t)(lo + (byte_off >> 4)); }
+};
+__device__ __forceinline__ UmmaDesc umma_desc2(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  UmmaDesc d;
+  d.lo = ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+  d.hi = (sbo_bytes >> 4) | (1u << 14);
+  return d;
+}
+// one lane of a converged warp (the MMA issuer): unlike `if (lane == 0)` the compiler then knows the predicate is
+// warp-uniform and emits the tensor-core instructions without a per-lane election loop around each of them
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
 // instruction descriptor: D fp32, A/B tf32 (fmt 2) or bf16 (fmt 1), both K-major, M = 128
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t fmt, int n) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
