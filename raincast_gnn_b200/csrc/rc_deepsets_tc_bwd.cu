@@ -10,9 +10,9 @@
 // Roles (14 warps): 8 x E1 (two per TMEM lane quarter, 32 of the stage's 64 columns each), 4 x converter (raw member
 // rows -> B1 = E as [row][feature] K-major and B2 = E^T as [feature][row] K-major, hi | lo), the MMA issuer, the loader
 // (one bulk copy of the stage's contiguous member rows per stage - TMA engine, cp.async.bulk).
-// Pipelines: raw ring (3) -> B1|B2 ring (3) -> D1 (2 in TMEM) -> A2 (2 in TMEM) -> D2 (2 in TMEM).  The D2 accumulator
-// takes two stages (<= 48 accumulating MMAs: the tensor core truncates every accumulation, rc_gemm_tc.cu) and is then
-// flushed by the E1 warps into round-to-nearest register sums while the next two stages accumulate into the other one.
+// Pipelines: raw ring (3) -> B1|B2 ring (3) -> D1 (2 in TMEM) -> A2 (2 in TMEM) -> D2 (2 in TMEM).  A D2 accumulator
+// takes one stage (21 accumulating MMAs: the tensor core truncates every accumulation, rc_gemm_tc.cu) and is then
+// flushed by the E1 warps into round-to-nearest register sums while the next stage accumulates into the other one.
 // The member count is compile-time (the reference's ensembles: 11 reforecast / 51 forecast members), so the station of
 // a column is static; other member counts take the SIMT kernel (rc_deepsets.cu).
 #include <cuda_bf16.h>
@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
     const uint32_t a1_lo_off = a1_floats * 4;
     auto mma2 = [&](int i) {                                                // D2 += dh(stage i) . E(stage i)
       const uint32_t ab = i & 1, aph = (i >> 1) & 1, bb = i % kDbBuf;
-      const uint32_t pair = (i >> 1) & 1, pph = (i >> 2) & 1;
+      const uint32_t pair = i & 1, pph = (i >> 1) & 1;                       // one D2 accumulator per stage, alternating
       mbar_wait(bar(DB_A2_FULL + ab), aph);
-      if ((i & 1) == 0) mbar_wait(bar(DB_D2_EMPTY + pair), pph ^ 1);         // first stage of a pair: the accumulator was flushed
+      mbar_wait(bar(DB_D2_EMPTY + pair), pph ^ 1);                           // the accumulator was flushed
       tc_fence_after();
       if (lane == 0) db_trace(p.trace, 3, i);
       const uint32_t a_hi = t_a2 + ab * 128, a_lo = a_hi + 64, d2 = t_d2 + pair * 64;
@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
 #pragma unroll
         for (int ks = 0; ks < KS2; ++ks) {
           const uint32_t off = ks * 2 * lbo;
-          umma_tf32_ts(d2, a_lo + ks * 8, bh.at(off), idesc2, ((i & 1) == 0 && ks == 0) ? 0u : 1u);
+          umma_tf32_ts(d2, a_lo + ks * 8, bh.at(off), idesc2, ks == 0 ? 0u : 1u);
           if (!p.bf16) umma_tf32_ts(d2, a_hi + ks * 8, bh.at(b_lo_off + off), idesc2, 1u);
           umma_tf32_ts(d2, a_hi + ks * 8, bh.at(off), idesc2, 1u);
         }
         umma_commit(bar(DB_B_EMPTY + bb));
         umma_commit(bar(DB_A2_EMPTY + ab));
-        if ((i & 1) == 1 || i == n_my - 1) umma_commit(bar(DB_D2_FULL + pair));
+        umma_commit(bar(DB_D2_FULL + pair));
       }
       __syncwarp();
     };
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
     float sums[32];                                   // D2 columns [32*half, 32*half + 32) of this channel (half 1: 16 used)
 #pragma unroll
     for (int e = 0; e < 32; ++e) sums[e] = 0.f;
-    auto flush = [&](int pair_idx) {                  // add the D2 accumulator of stage pair `pair_idx` into the register sums
+    auto flush = [&](int pair_idx) {                  // add the D2 accumulator of stage `pair_idx` into the register sums
       const uint32_t pair = pair_idx & 1, pph = (pair_idx >> 1) & 1;
       mbar_wait(bar(DB_D2_FULL + pair), pph);
       tc_fence_after();
@@ -382,15 +382,10 @@ __global__ void __launch_bounds__(kDbThreads, 1) deepsets_pool_bwd_tc_kernel(con
         mbar_arrive(bar(DB_A2_FULL + db));
       }
       if (warp == 0) db_trace(p.trace, 5, i);
-      if (i >= 2 && (i & 1) == 0) flush((i >> 1) - 1);  // the pair that ended two stages ago has long completed
+      if (i >= 1) flush(i - 1);                         // MMA2 of the previous stage was issued when this stage's D1 was: long completed
       if (warp == 0) db_trace(p.trace, 6, i);
     }
-    // remaining pairs: (n_my + 1) / 2 pairs in total
-    {
-      const int n_pairs = (n_my + 1) >> 1;
-      const int done = n_my >= 3 ? ((n_my - 1) >> 1) : 0;     // pairs flushed inside the loop
-      for (int pi = done; pi < n_pairs; ++pi) flush(pi);
-    }
+    if (n_my >= 1) flush(n_my - 1);
     // partials[blockIdx.x][hidden*feats + hidden]: d W1 [channel][feature] and d b1 [channel] of this CTA's stages
     float* out = p.partials + (size_t)blockIdx.x * ((size_t)p.hidden * F + p.hidden);
     if (cok) {

@@ -24,10 +24,12 @@
 //
 // Accumulation chains.  The tensor core adds every MMA's 8-term dot product into the fp32 accumulator with truncation
 // (round toward zero): a chain of L accumulating MMAs shrinks the result by ~L * 3e-8 relative (measured: 1.2e-5 on a
-// weight gradient over 1900 samples per CTA).  So no accumulator ever takes more than kTcChain = 4 stages (48 MMAs, ~1.5e-6):
-// the rows kernel gives every group of 4 k-blocks its own accumulator and the epilogue adds the groups (K <= 512), the
-// wgrad kernel flushes its accumulator into round-to-nearest register sums every 4 sample blocks (two accumulators, so
-// the flush of one overlaps the MMAs into the other).
+// weight gradient over 1900 samples per CTA; 1.0 - 1.5e-5 on the first layers' gradients of the config-4 model, whose
+// backward chains ten such GEMMs, with chains of 48).  So no accumulator takes more than 2 stages (24 MMAs, ~4e-7):
+// the rows kernel gives every group of 2 k-blocks its own accumulator and the epilogue adds the groups (K <= 256; wider
+// layers - config 5, a bf16 / 1e-2 configuration - use groups of 4), the wgrad kernel flushes its accumulator into
+// round-to-nearest register sums every 2 sample blocks (two accumulators, so the flush of one overlaps the MMAs into the
+// other).
 #include <stdlib.h>
 
 #include "rc_gemm_tile.cuh"
@@ -46,7 +48,7 @@ constexpr int kTcBlkFloats = 128 * 32;                               // one hi (
 constexpr int kTcBlkBytes = kTcBlkFloats * 4;
 constexpr int kTcStageBytes = 4 * kTcBlkBytes;                       // A hi | A lo | B hi | B lo
 constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 256 + 1024 + 128;  // + barriers, + column sums, + alignment slack
-constexpr int kTcChain = 4;                                          // stages accumulated into one TMEM accumulator
+constexpr int kTcChain = 2;                                          // stages accumulated into one TMEM accumulator (wgrad; rows: TcRowsP::chain)
 constexpr int kTcWgEpiWarps = 8;                                     // wgrad: two epilogue warps per TMEM lane quarter
 constexpr int kTcWgThreads = 32 * (kTcWgEpiWarps + kTcProdWarps + 1);
 constexpr uint32_t kTcLBO = 128, kTcSBO = 1024;
@@ -141,6 +143,7 @@ struct TcRowsP {
   const float* wpack;
   int kb1, kblocks, n_tiles, row_tiles;
   int a_vec, a2_vec;
+  int chain;                 // k-blocks per accumulator: 2, or 4 when K > 256 (at most four accumulators per tile)
   long long* trace;          // debug (rc_debug_tc_trace): CTA 0 records [role][tile][begin, end] clocks; NULL in production
   int dbg;                   // debug (RC_TC_DBG): 2 = one accumulator set (no MMA / epilogue overlap)
 };
@@ -288,7 +291,7 @@ __device__ __forceinline__ void tc_rows_producer(const TcRowsP& p, const TcSmem&
         }
       }
       float4 hi, lo;
-      split_tf32_trunc(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+      split_tf32_rn(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
       st4(bh + sidx_f(it), hi);
       st4(bl + sidx_f(it), lo);
     }
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_rows_kernel(const TcRow
   const rc_gemm& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles_total = p.row_tiles * p.n_tiles;
-  const int groups = ceil_div(p.kblocks, kTcChain);        // accumulators per tile (<= 4; 1 with the weight tile in TMEM)
+  const int groups = ceil_div(p.kblocks, p.chain);         // accumulators per tile (<= 4; 1 with the weight tile in TMEM)
   const uint32_t nbuf = (groups <= 2 && !(p.dbg & 2)) ? 2u : 1u;   // accumulator sets: tile t+1's MMAs overlap tile t's epilogue
   constexpr uint32_t kStages = ATM ? kTcStagesAtm : kTcStages;
   constexpr int kStageBytes = ATM ? 2 * kTcBlkBytes : kTcStageBytes;
@@ -491,13 +494,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_rows_kernel(const TcRow
       if (lane == 0) tc_trace(p.trace, 1, tcount, 0);
       for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
         const uint32_t s = cnt % kStages, ph = (cnt / kStages) & 1;
-        const uint32_t tmem_d = tmem_base + (acc * groups + kb / kTcChain) * 128;
+        const uint32_t tmem_d = tmem_base + (acc * groups + kb / p.chain) * 128;
         mbar_wait(sm.full + 8 * s, ph);
         tc_fence_after();
         const uint32_t st = smem_u32(sm.stages + (size_t)s * kStageBytes);
         if (elect_one()) {
-          if (ATM) tc_issue_stage_atm(st, w_tmem + kb * 32, tmem_d, idesc, kb % kTcChain == 0);
-          else tc_issue_stage(st, tmem_d, idesc, kb % kTcChain == 0);
+          if (ATM) tc_issue_stage_atm(st, w_tmem + kb * 32, tmem_d, idesc, kb % p.chain == 0);
+          else tc_issue_stage(st, tmem_d, idesc, kb % p.chain == 0);
           umma_commit(sm.empty + 8 * s);
           if (kb == p.kblocks - 1) umma_commit(sm.tmem_full + 8 * acc);
         }
@@ -716,10 +719,10 @@ __global__ void __launch_bounds__(kTcWgThreads, 1) gemm_tc_wgrad_kernel(const Tc
         const int c = q * 2 + (pw >> 2);
         const int idx = (il >> 3) * 256 + c * 32 + (il & 7) * 4;
         float4 hi, lo;
-        split_tf32_trunc(va[q], hi, lo);
+        split_tf32_rn(va[q], hi, lo);
         st4(ah + idx, hi);
         st4(al + idx, lo);
-        split_tf32_trunc(vb[q], hi, lo);
+        split_tf32_rn(vb[q], hi, lo);
         st4(bh + idx, hi);
         st4(bl + idx, lo);
       }
@@ -816,7 +819,7 @@ static bool tc_atm_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("RC_GEMM_TC_ATMEM");
-    on = (e && atoi(e) == 0) ? 0 : 1;
+    on = (e && atoi(e) != 0) ? 1 : 0;
   }
   return on == 1;
 }
@@ -827,7 +830,7 @@ int gemm_tc_kind(const rc_gemm* g) {
   if (g->a_layout == RC_A_ROW) {
     if (g->m < kTcMinRows || g->splits > 1 || g->b.op != RC_OP_NONE || g->colsum_a) return 0;
     if (g->k + g->k2 < 32) return 0;
-    if (ceil_div(g->k, 32) + (g->k2 > 0 ? ceil_div(g->k2, 32) : 0) > 4 * kTcChain) return 0;   // four accumulators per tile at most
+    if (ceil_div(g->k, 32) + (g->k2 > 0 ? ceil_div(g->k2, 32) : 0) > 16) return 0;   // four accumulators of four k-blocks per tile at most
     return 1;
   }
   if (g->a_layout == RC_A_RED && g->b_layout == RC_B_RED) {
@@ -883,8 +886,12 @@ int gemm_tc_run(const rc_gemm* g, cudaStream_t s) {
     p.wpack = nullptr;
     int grid = p.row_tiles * p.n_tiles;
     if (grid > kNumSMs) grid = kNumSMs;
-    // one output tile wide, K <= 128: the weight tile lives in TMEM for the whole kernel (no packing pass, no workspace use)
-    if (p.n_tiles == 1 && p.kblocks <= kTcChain && g->k2 == 0 && tc_atm_enabled()) {
+    p.chain = p.kblocks <= 8 ? 2 : 4;
+    // one output tile wide, K <= 128: the weight tile can live in TMEM for the whole kernel (no packing pass); it leaves
+    // room for ONE accumulator per tile only, i.e. chains of 48 MMAs: opt-in (RC_GEMM_TC_ATMEM=1), measured 39 us against
+    // 44 us for a 100k x 128 x 128 Linear, not worth 1e-6 of systematic error per layer
+    if (p.n_tiles == 1 && p.kblocks <= 4 && g->k2 == 0 && tc_atm_enabled()) {
+      p.chain = 4;
       launch_pdl(gemm_tc_rows_kernel<true>, dim3(grid), dim3(kTcThreads), (size_t)kTcSmemBytes, s, p);
       return check_launch("gemm_tc_rows_kernel");
     }

@@ -148,6 +148,13 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& l
   lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 
+// round-to-nearest split without cvt.rna's NaN / Inf handling (three instructions per element; finite inputs):
+// hi = (bits + 2^12) & ~(2^13 - 1), |lo| <= 2^-12 |v| with either sign, so the tensor core's truncation of lo is unbiased
+__device__ __forceinline__ void split_tf32_rn(const float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); hi.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u);
+  hi.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); hi.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
 // the same split with hi = v truncated to TF32 (two instructions per element instead of five; hi exact in 11 bits, lo the
 // remaining 13 bits of which the tensor core keeps 11: error <= 2^-22 per product, well inside the 1e-5 budget)
 __device__ __forceinline__ void split_tf32_trunc(const float4 v, float4& hi, float4& lo) {

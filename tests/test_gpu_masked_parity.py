@@ -98,3 +98,114 @@ def test_reference_shape_mask_matched_gradients(dev, members):
         worst[k] = (gr.cpu().double() - g64[k]).abs().max().item() / scale
     bad = {k: v for k, v in worst.items() if not v < TOL}
     assert not bad, f"gradient tensors beyond {TOL} with the ReLU decisions matched: {bad}"
+
+
+# ------------------------------------------------------------------------------------------------ configs 4 and 5 at scale
+def _scaled_case(dev, members, hidden, n=100_000, feats=35, layers=4):
+    """BASELINE.json config 4 shape: ONE station graph of 100 000 nodes (uniform in a 1000 x 1000 box, radius giving
+    2 978 560 edges incl. self loops), `members` ensemble members, one graph per step."""
+    from raincast_gnn_b200 import graph as G
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.pyg_compat import Data
+    ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
+    if n == 100_000:
+        assert ei.shape[1] == 2_978_560                      # SURVEY.md 8d: confirms the generator
+    sg = G.build_station_graph(ei, ea, n).to(dev)
+    x, ens = syn.node_features(n, members, feats, seed=3)
+    y = syn.log_precip_targets(n, seed=3)
+    kw = dict(in_channels=feats, hidden_channels_gnn=hidden, out_channels_gnn=hidden, num_layers_gnn=layers,
+              optimizer_class=torch.optim.AdamW, optimizer_params={"lr": 1e-4}, loss="MixedLoss", grad_u="True", u=1.71, xi=0.5)
+    model = GNN(**kw)
+    sd = syn.seeded_state_dict(model.state_dict(), seed=99)
+    model.load_state_dict(sd)
+    data = Data(x=x, ensemble=ens, edge_index=ei, edge_attr=ea, y=y)
+    dd = data.to(dev)
+    dd.station_graph = sg
+    return data, dd, model.to(dev).train(), sd, kw
+
+
+def _to_cpu(tree):
+    return {k: v.detach().cpu() for k, v in tree.items()}
+
+
+def test_config4_scaled_graph_mask_matched(dev):
+    """BASELINE.json config 4 (100k nodes, 2 978 560 edges, 51 members, H=128, L=4, fp32) through the module API: the
+    tiled aggregation, the tensor-core Linear layers and the tensor-core DeepSets forward / backward all run here.
+    preds / CRPS at 1e-5 against the float64 oracle; every gradient at 1e-5 with the ReLU decisions matched."""
+    from oracle import masked
+    from raincast_gnn_b200 import kernels as K
+    data, dd, model, sd, kw = _scaled_case(dev, 51, 128)
+    assert dd.station_graph.tiles(128) is not None, "config 4 must take the station-tile aggregation"
+    K.MASKS.active = {}
+    try:
+        preds = model(dd)
+        loss = model.loss_fn.crps(preds, dd.y)
+        loss.backward()
+        torch.cuda.synchronize()
+        dump = K.MASKS.active
+    finally:
+        K.MASKS.active = None
+    h, m, em = 128, data.x.shape[0], 51
+    masks = {"phi": K.unpack_bits(dump["phi"], h).reshape(m, em, h), "rho": dump["rho"]}
+    t_perm = dd.station_graph.t_perm.long()
+    for i, lm in enumerate(dump["layers"][::-1]):
+        msg_t = K.unpack_bits(lm["msg"], h)
+        msg = torch.empty_like(msg_t)
+        msg[t_perm] = msg_t
+        masks[f"msg{i}"] = msg
+        masks[f"bn{i}"] = K.unpack_bits(lm["bn"], h)
+        masks[f"out{i}"] = K.unpack_bits(lm["out"], h)
+        del msg_t
+    grads = {k: p.grad.detach().double().cpu() for k, p in model.named_parameters()}
+    preds, loss = preds.detach().cpu(), float(loss)
+    del dump
+    torch.cuda.empty_cache()
+    # float64 oracle on the same device (plain torch ops; ~60 GB of float64 activations at this size)
+    args = dict(num_layers=4, loss=kw["loss"], grad_u=kw["grad_u"], u=kw["u"], xi=kw["xi"], device=dev)
+    p64, l64, g64, _ = masked.loss_and_grads(sd, data, masks=masks, **args)
+    p64, l64, g64 = p64.cpu(), float(l64), _to_cpu(g64)
+    del masks
+    torch.cuda.empty_cache()
+    _, _, _, own = masked.loss_and_grads(sd, data, **args)
+    assert rel_err(preds.numpy(), p64.numpy()) < TOL
+    assert abs(loss - l64) < TOL * abs(l64)
+    worst = {}
+    for k, gr in grads.items():
+        scale = grad_scale(k, g64[k].abs().max().item(), lambda kk: g64[kk].abs().max().item())
+        worst[k] = (gr - g64[k]).abs().max().item() / scale
+    bad = {k: v for k, v in worst.items() if not v < TOL}
+    assert not bad, f"config 4: gradient tensors beyond {TOL} with the ReLU decisions matched: {bad}"
+
+
+def test_config5_bf16_wide_hidden_at_config4_shape(dev):
+    """BASELINE.json config 5 at the config-4 shape: bf16 DeepSets member contraction (tcgen05 kind::f16 forward, the
+    tensor-core backward on bf16-rounded operands), hidden 512, 4 GINE layers in fp32 (tensor-core 3xTF32 Linear layers
+    with K = 512), 100k nodes / 2 978 560 edges / 51 members.  Tolerance 1e-2 (north_star, bf16) against the fp32 oracle
+    evaluated on what the tensor cores see (ensemble and phi[0].weight rounded to bf16)."""
+    from oracle import masked
+    data, dd, model, sd, kw = _scaled_case(dev, 51, 512)
+    sd_r = dict(sd)
+    sd_r["deepset.phi.0.weight"] = sd["deepset.phi.0.weight"].bfloat16().float()
+    import copy
+    data_r = copy.copy(data)
+    data_r.ensemble = data.ensemble.bfloat16().float()
+    args = dict(num_layers=4, loss=kw["loss"], grad_u=kw["grad_u"], u=kw["u"], xi=kw["xi"], device=dev, dtype=torch.float32)
+    p_ref, l_ref, g_ref, _ = masked.loss_and_grads(sd_r, data_r, **args)      # ~100 GB of fp32 activations: first, then freed
+    p_ref, l_ref, g_ref = p_ref.cpu(), float(l_ref), _to_cpu(g_ref)
+    torch.cuda.empty_cache()
+    model.deepset.compute_dtype = "bf16"
+    preds = model(dd)
+    loss = model.loss_fn.crps(preds, dd.y)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(preds.detach().cpu().numpy(), p_ref.numpy()) < 1e-2
+    assert abs(float(loss) - l_ref) < 1e-2 * abs(l_ref)
+    bad = []
+    for k, v in model.named_parameters():
+        if k.endswith(".nn.0.bias"):
+            continue
+        d = v.grad.cpu().double() - g_ref[k].double()
+        l2 = (d.norm() / g_ref[k].double().norm()).item()
+        if l2 >= (2e-2 if v.numel() == 1 else 1e-2):          # scalar eps: one ReLU-threshold unit moves it by ~1e-2
+            bad.append((k, round(l2, 5)))
+    assert not bad, bad
