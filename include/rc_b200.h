@@ -163,6 +163,13 @@ int rc_gine_aggr_bwd_tiled(const float* g, const float* x, const rc_gine_tiles* 
 #define RC_OP_BN_RELU 1 /* v = relu((v - p0[col]) * p1[col] * p2[col] + p3[col])   (mean, rstd, gamma, beta) */
 #define RC_OP_BITMASK 2 /* v = bit(bits[row*ld_bits + col/32], col%32) ? v : 0                                */
 #define RC_OP_AFFINE2 3 /* v = p0[col]*v + p1[col]*(aux[row*ld_aux + col] - p3[col]) + p2[col]  (BN backward) */
+/* The GINE aggregation as the prologue of the layer's first Linear (north_star item 2: message, aggregation and the
+ * (1+eps) x_i + aggr update fused into the node MLP; models/gnn.py:21-29 / PyG GINEConv): A operand only, A stored [i][r],
+ *   A(i, r) = sum_{slot s of CSR row i} relu(x[idx1[s], r] + aux[s]*p0[r] + p1[r]) + (1 + p2[0]) * x[i, r]
+ * with ptr = x (the layer input, ld % 4 == 0, 16-byte aligned), idx0 = rowptr, idx1 = col, aux = attr, p0 / p1 = the edge
+ * Linear's weight / bias, p2 = eps.  Same arithmetic and slot order as rc_gine_aggr_fwd (bit-identical).  rc_gemm.a_out
+ * (optional) receives the aggregated rows - the backward needs them for the weight gradient. */
+#define RC_OP_GINE_AGGR 4
 
 /* epilogues on D element (i, j), after `+ bias_scale*bias[j]` */
 #define RC_EPI_NONE 0
@@ -181,6 +188,7 @@ typedef struct rc_operand {
   const float* p0; const float* p1; const float* p2; const float* p3;   /* per stored column */
   const float* aux; int ld_aux;
   const uint32_t* bits; int ld_bits;
+  const int32_t* idx0; const int32_t* idx1;   /* RC_OP_GINE_AGGR: CSR rowptr / col */
 } rc_operand;
 
 typedef struct rc_gemm {
@@ -209,6 +217,7 @@ typedef struct rc_gemm {
    * call), and for weight-gradient GEMMs (A stored [r][i], B stored [r][j]) with k >= 16384 samples (no workspace).
    * RC_GEMM_TC=0 in the environment keeps everything on the SIMT kernels. */
   void* tc_ws; size_t tc_ws_bytes;
+  float* a_out; int ld_a_out;   /* RC_OP_GINE_AGGR: the A operand after its prologue, written once (nullable) */
 } rc_gemm;
 
 int rc_gemm_row_tile(const rc_gemm* g);  /* the row tile the launch would use (for stats sizing)   */
@@ -326,6 +335,16 @@ int rc_p2p_barrier(int32_t* const* flags, int32_t* epochs, int rank, int world, 
 int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, float* exp_avg, float* exp_avg_sq,
                       int64_t* step, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                       void* stream);
+/* The same exchange as ONE kernel after backward: rc_p2p_step waits (inside the kernel) until every rank has published
+ * its gradients of exchange *epoch + 1, sums them in rank order, applies AdamW, advances *step and *epoch and publishes
+ * "done reading"; rc_p2p_wait_done - launched at the start of the NEXT step, off the critical path - waits until every
+ * peer is done reading this rank's gradients before they are overwritten.  flags: as rc_p2p_barrier (slot 0 = published,
+ * slot 1 = done reading); epoch: this rank's int32[1], zero before first use, never reset (it must advance in lock step
+ * on all ranks: every rank calls rc_p2p_step the same number of times). */
+int rc_p2p_step(float* param, const float* const* peer_grads, int32_t* const* flags, int32_t* epoch, int rank, int world,
+                float* exp_avg, float* exp_avg_sq, int64_t* step, long long n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int32_t* timed_out, void* stream);
+int rc_p2p_wait_done(int32_t* const* flags, const int32_t* epoch, int rank, int world, int32_t* timed_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Test instrumentation: the ReLU decisions of the backward kernels as bit masks (bit c % 32 of word c / 32 per row).

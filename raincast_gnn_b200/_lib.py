@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("RC_B200_LIB") or os.path.join(_HERE, "csrc", "librc_b
 
 RC_A_ROW, RC_A_RED = 0, 1
 RC_B_COL, RC_B_RED = 0, 1
-RC_OP_NONE, RC_OP_BN_RELU, RC_OP_BITMASK, RC_OP_AFFINE2 = 0, 1, 2, 3
+RC_OP_NONE, RC_OP_BN_RELU, RC_OP_BITMASK, RC_OP_AFFINE2, RC_OP_GINE_AGGR = 0, 1, 2, 3, 4
 RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_EPI_BN_STATS, RC_EPI_MASK_POS, RC_EPI_BN_RELU_BWD, RC_EPI_ADD_RES = 0, 1, 2, 3, 4, 5, 6
 RC_LOSS_NORMAL, RC_LOSS_MIXED_NORMAL, RC_LOSS_MIXED, RC_LOSS_MIXED_U = 0, 1, 2, 3
 
@@ -36,7 +36,7 @@ class rc_gine_tiles(C.Structure):
 
 class rc_operand(C.Structure):
     _fields_ = [("ptr", _fp), ("ld", C.c_int), ("op", C.c_int), ("p0", _fp), ("p1", _fp), ("p2", _fp), ("p3", _fp),
-                ("aux", _fp), ("ld_aux", C.c_int), ("bits", _fp), ("ld_bits", C.c_int)]
+                ("aux", _fp), ("ld_aux", C.c_int), ("bits", _fp), ("ld_bits", C.c_int), ("idx0", _fp), ("idx1", _fp)]
 
 
 class rc_gemm(C.Structure):
@@ -47,7 +47,7 @@ class rc_gemm(C.Structure):
                 ("res", _fp), ("ld_res", C.c_int), ("bits_out", _fp), ("ld_bits_out", C.c_int),
                 ("e_aux", _fp), ("ld_e_aux", C.c_int), ("e_p0", _fp), ("e_p1", _fp), ("e_p2", _fp), ("e_p3", _fp),
                 ("stats", _fp), ("splits", C.c_int), ("split_stride", C.c_longlong), ("colsum_a", _fp),
-                ("rows_per_warp", C.c_int), ("tc_ws", _fp), ("tc_ws_bytes", C.c_size_t)]
+                ("rows_per_warp", C.c_int), ("tc_ws", _fp), ("tc_ws_bytes", C.c_size_t), ("a_out", _fp), ("ld_a_out", C.c_int)]
 
 
 class rc_reduce_seg(C.Structure):
@@ -101,6 +101,8 @@ def _declare(lib):
         "rc_gather_dates": (i, [p, p, p, p, i, i, ll, ll, ll, p, p, p, p, p]),
         "rc_p2p_barrier": (i, [p, p, i, i, i, p, p]),
         "rc_p2p_adamw_step": (i, [p, p, i, p, p, p, ll, f, f, f, f, f, p]),
+        "rc_p2p_step": (i, [p, p, p, p, i, i, p, p, p, ll, f, f, f, f, f, p, p]),
+        "rc_p2p_wait_done": (i, [p, p, i, i, p, p]),
         "rc_debug_gine_msg_mask": (i, [p, p, p, p, p, i, i, i, p, p]),
         "rc_debug_bn_relu_mask": (i, [p, i, p, p, p, p, i, i, p, p]),
         "rc_debug_tc_trace": (None, [p]),

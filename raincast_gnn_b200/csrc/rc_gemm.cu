@@ -124,6 +124,14 @@ extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
   if (g->splits > 1 && g->epi != RC_EPI_NONE) return fail(RC_ERR_ARG, "rc_gemm_run: split reduction only with RC_EPI_NONE");
   if (g->splits > 1 && g->bias) return fail(RC_ERR_ARG, "rc_gemm_run: split reduction cannot add a bias");
   if (g->colsum_a && g->a_layout != RC_A_RED) return fail(RC_ERR_ARG, "rc_gemm_run: colsum_a needs A stored [r][i]");
+  if (g->a.op == RC_OP_GINE_AGGR) {
+    if (g->a_layout != RC_A_ROW || !g->a.idx0 || !g->a.idx1 || !g->a.aux || !g->a.p0 || !g->a.p1 || !g->a.p2)
+      return fail(RC_ERR_ARG, "rc_gemm_run: RC_OP_GINE_AGGR needs A stored [i][r] and rowptr / col / attr / w_edge / b_edge / eps");
+    if (g->k % 4 || g->a.ld % 4 || !aligned16(g->a.ptr) || !aligned16(g->a.p0) || !aligned16(g->a.p1) ||
+        (g->a_out && (g->ld_a_out % 4 || !aligned16(g->a_out))))
+      return fail(RC_ERR_ARG, "rc_gemm_run: RC_OP_GINE_AGGR needs 4 | k, 4 | ld and 16-byte aligned x, w_edge, b_edge, a_out");
+  }
+  if (g->b.op == RC_OP_GINE_AGGR) return fail(RC_ERR_ARG, "rc_gemm_run: RC_OP_GINE_AGGR is an A-operand prologue");
   if (g->m == 0 || g->n == 0) return RC_OK;
   {
     const int tc = gemm_tc_kind(g);

@@ -828,7 +828,7 @@ static bool tc_atm_enabled() {
 int gemm_tc_kind(const rc_gemm* g) {
   if (!tc_enabled() || g->m <= 0 || g->n <= 0) return 0;
   if (g->a_layout == RC_A_ROW) {
-    if (g->m < kTcMinRows || g->splits > 1 || g->b.op != RC_OP_NONE || g->colsum_a) return 0;
+    if (g->m < kTcMinRows || g->splits > 1 || g->b.op != RC_OP_NONE || g->colsum_a || g->a.op == RC_OP_GINE_AGGR) return 0;
     if (g->k + g->k2 < 32) return 0;
     if (ceil_div(g->k, 32) + (g->k2 > 0 ? ceil_div(g->k2, 32) : 0) > 16) return 0;   // four accumulators of four k-blocks per tile at most
     return 1;

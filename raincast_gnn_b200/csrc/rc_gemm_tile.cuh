@@ -1,6 +1,7 @@
 // GEMM tile function shared by the standalone kernel (rc_gemm.cu) and the step program (rc_prog.cu).
 #pragma once
 #include "rc_common.cuh"
+#include "rc_gine_tile.cuh"
 
 namespace rc {
 
@@ -23,7 +24,7 @@ __device__ __forceinline__ float apply_op(const rc_operand& o, float v, int row,
       return ((__ldg(o.bits + (size_t)row * o.ld_bits + (col >> 5)) >> (col & 31)) & 1u) ? v : 0.f;
     case RC_OP_AFFINE2:
       return fmaf(__ldg(o.p0 + col), v, fmaf(__ldg(o.p1 + col), __ldg(o.aux + (size_t)row * o.ld_aux + col) - __ldg(o.p3 + col), __ldg(o.p2 + col)));
-    default:
+    default:      // (RC_OP_GINE_AGGR never comes here: gemm_tile builds that operand with gine_aggr4)
       return v;
   }
 }
@@ -49,6 +50,37 @@ __device__ __forceinline__ float4 load_op4(const rc_operand& o, const float* bas
     if (col + 3 < ncols) v.w = apply_op(o, v.w, row, col + 3);
   }
   return v;
+}
+
+// RC_OP_GINE_AGGR: four consecutive columns of the aggregated row (PyG GINEConv message + 'add' aggregation + self term),
+// same arithmetic and slot order as gine_fwd_tile (rc_gine_tile.cuh).  The lanes that share a row walk its edge list
+// together: with 128-long reduction slices that is a whole warp gathering one 512-byte source row per edge.
+__device__ __forceinline__ float4 gine_aggr4(const rc_operand& o, int row, int col, int nrows, int ncols) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= nrows || col >= ncols) return acc;
+  const float* __restrict__ x = o.ptr;
+  const float4 w4 = ldg4(o.p0 + col), b4 = ldg4(o.p1 + col);
+  const int beg = __ldg(o.idx0 + row), end = __ldg(o.idx0 + row + 1);
+  int s = beg;
+  for (; s + kEdgeUnroll <= end; s += kEdgeUnroll) {     // 4 independent row gathers in flight
+    int src[kEdgeUnroll];
+    float a[kEdgeUnroll];
+    float4 v[kEdgeUnroll];
+#pragma unroll
+    for (int k = 0; k < kEdgeUnroll; ++k) { src[k] = __ldg(o.idx1 + s + k); a[k] = __ldg(o.aux + s + k); }
+#pragma unroll
+    for (int k = 0; k < kEdgeUnroll; ++k) v[k] = ldg4(x + (size_t)src[k] * o.ld + col);
+#pragma unroll
+    for (int k = 0; k < kEdgeUnroll; ++k) add4(acc, relu_msg(v[k], a[k], w4, b4));
+  }
+  for (; s < end; ++s) {
+    const int src = __ldg(o.idx1 + s);
+    const float a = __ldg(o.aux + s);
+    add4(acc, relu_msg(ldg4(x + (size_t)src * o.ld + col), a, w4, b4));
+  }
+  const float self_scale = 1.0f + __ldg(o.p2);
+  const float4 xi = ldg4(x + (size_t)row * o.ld + col);
+  return make_float4(acc.x + self_scale * xi.x, acc.y + self_scale * xi.y, acc.z + self_scale * xi.z, acc.w + self_scale * xi.w);
 }
 
 // One CTA tile of the GEMM: `bid` plays blockIdx (x: row tile, y: column tile, z: reduction split), `smem` is the
@@ -112,7 +144,10 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
       const int s = tid + it * kGemmThreads;
       if (A_SLOTS >= kGemmThreads || s < A_SLOTS) {
         const int row = s / A_F4_PER_ROW, c4 = (s % A_F4_PER_ROW) * 4;
-        if (AL == RC_A_ROW) ra[it] = load_op4(g.a, abase, lda, m0 + row, k0 + c4, g.m, kk, avec, !seg2);
+        if (AL == RC_A_ROW && g.a.op == RC_OP_GINE_AGGR && !seg2) {
+          ra[it] = gine_aggr4(g.a, m0 + row, k0 + c4, g.m, kk);
+          if (g.a_out != nullptr && bid.y == 0 && m0 + row < g.m && k0 + c4 < kk) st4(g.a_out + (size_t)(m0 + row) * g.ld_a_out + k0 + c4, ra[it]);
+        } else if (AL == RC_A_ROW) ra[it] = load_op4(g.a, abase, lda, m0 + row, k0 + c4, g.m, kk, avec, !seg2);
         else                ra[it] = load_op4(g.a, abase, lda, k0 + row, m0 + c4, kk, g.m, avec, !seg2);
       }
     }

@@ -139,11 +139,7 @@ extern "C" int rc_adamw_step(float* param, const float* grad, float* exp_avg, fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long blocks = ceil_div_ll(n > 0 ? n : 1, 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  const AdamTickP pt{reinterpret_cast<long long*>(step)};
   const AdamP pa{param, grad, exp_avg, exp_avg_sq, reinterpret_cast<long long*>(step), n, lr, beta1, beta2, eps, weight_decay, grad_scale};
-  launch_pdl(adamw_tick_kernel, dim3(1), dim3(32), 0, s, pt);
-  if (int e = check_launch("adamw_tick_kernel")) return e;
-  if (n == 0) return RC_OK;
-  launch_pdl(adamw_kernel, dim3((int)blocks), dim3(256), 0, s, pa);
+  launch_pdl(adamw_kernel, dim3((int)blocks), dim3(256), 0, s, pa);     // (n == 0: one CTA that only advances the step counter)
   return check_launch("adamw_kernel");
 }

@@ -53,7 +53,7 @@ struct AdamP {
   const float* grad;
   float* exp_avg;
   float* exp_avg_sq;
-  const long long* step;
+  long long* step;            // steps taken so far; this launch is step[0] + 1 and the last CTA to finish writes it back
   long long n;
   float lr;
   float beta1;
@@ -270,6 +270,21 @@ __device__ __forceinline__ void adamw_tick_tile(const AdamTickP& p, const uint3 
   if (threadIdx.x == 0) step[0] += 1;
 }
 
+// The step counter is read by every CTA at its start and advanced by the CTA that finishes last (a device-wide
+// arrival counter that leaves itself at zero): one launch per optimiser step, replayable inside a CUDA graph.
+static __device__ unsigned int g_adamw_arrivals = 0;
+__device__ __forceinline__ void adamw_finish(long long* step, unsigned int n_ctas) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&g_adamw_arrivals, 1u) == n_ctas - 1) {
+      g_adamw_arrivals = 0;
+      step[0] += 1;
+      __threadfence();
+    }
+  }
+}
+
 __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, const uint3 gdim) {
   float* __restrict__ param = p.param;
   const float* __restrict__ grad = p.grad;
@@ -287,7 +302,7 @@ __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, cons
 
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
-    const double t = (double)step[0];
+    const double t = (double)(step[0] + 1);
     const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
     s_step_size = (float)((double)lr / bc1);
     s_bc2_sqrt = (float)sqrt(bc2);
@@ -304,6 +319,7 @@ __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, cons
     p = p - step_size * (m1 / denom);
     param[i] = p; exp_avg[i] = m1; exp_avg_sq[i] = v;
   }
+  adamw_finish(p.step, gdim.x);
 }
 
 

@@ -96,9 +96,136 @@ __global__ void __launch_bounds__(256) p2p_adamw_kernel(const P2pAdamP p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- fused exchange
+// The whole exchange as ONE kernel on the critical path (rc_p2p_step): every CTA starts by waiting until all ranks
+// have published gradient set number `epoch + 1` (CTA 0 publishes this rank's: one st.release.sys per peer), sums the
+// peers' gradients in rank order, applies AdamW, and the CTA that finishes last advances the Adam step counter and the
+// exchange epoch and tells the peers that this rank is done reading.  The matching wait ("every peer is done reading my
+// gradients: I may overwrite them") is rc_p2p_wait_done, which the engine launches at the START of the next step on its
+// side stream - it is over long before that step's backward writes its first gradient, i.e. off the critical path.
+// Replaces barrier -> tick -> sum + AdamW -> barrier (four dependent launches after backward).
+static __device__ unsigned int g_p2p_arrivals = 0;
+
+__global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* const* __restrict__ flags, int* __restrict__ epoch,
+                                                       int rank, int* __restrict__ timed_out) {
+  const AdamP& a = p.a;
+  __shared__ float s_step_size, s_bc2_sqrt;
+  const int ep = epoch[0] + 1;                     // (advanced only by the last CTA to finish)
+  if (threadIdx.x < p.world) {
+    const int q = threadIdx.x;
+    if (blockIdx.x == 0) {
+      __threadfence_system();                      // this device's earlier kernels' gradient writes, system wide
+      st_release_sys(flags[q] + rank, ep);         // slot 0 of rank q's block: "rank's gradients of exchange ep are in place"
+    }
+    const int* mine = flags[rank] + q;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < ep) {
+      if (clock64() - t0 > 20000000000ll) {        // ~10 s: a peer died; do not hang the device
+        atomicExch(timed_out, 1);
+        break;
+      }
+      __nanosleep(20);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const double t = (double)(a.step[0] + 1);
+    const double bc1 = 1.0 - pow((double)a.beta1, t), bc2 = 1.0 - pow((double)a.beta2, t);
+    s_step_size = (float)((double)a.lr / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float decay = 1.0f - a.lr * a.weight_decay, one_m_b1 = 1.0f - a.beta1, one_m_b2 = 1.0f - a.beta2;
+  const long long n4 = a.n / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.world; ++r) {            // fixed order: identical sums on every rank
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(p.grads[r]) + i);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    float4 w = reinterpret_cast<float4*>(a.param)[i], m1 = reinterpret_cast<float4*>(a.exp_avg)[i],
+           v2 = reinterpret_cast<float4*>(a.exp_avg_sq)[i];
+    float* gp = &g.x; float* wp = &w.x; float* mp = &m1.x; float* vp = &v2.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gp[j] * a.grad_scale;
+      float pj = wp[j] * decay;
+      mp[j] = mp[j] + (gj - mp[j]) * one_m_b1;                 // lerp_
+      vp[j] = vp[j] * a.beta2 + one_m_b2 * gj * gj;            // mul_ + addcmul_
+      const float denom = sqrtf(vp[j]) / bc2_sqrt + a.eps;
+      wp[j] = pj - step_size * (mp[j] / denom);
+    }
+    reinterpret_cast<float4*>(a.param)[i] = w;
+    reinterpret_cast<float4*>(a.exp_avg)[i] = m1;
+    reinterpret_cast<float4*>(a.exp_avg_sq)[i] = v2;
+  }
+  __syncthreads();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&g_p2p_arrivals, 1u) == gridDim.x - 1;
+    if (s_last) {
+      g_p2p_arrivals = 0;
+      a.step[0] += 1;
+      epoch[0] = ep;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < p.world) {
+    __threadfence_system();
+    st_release_sys(flags[threadIdx.x] + kMaxPeers + rank, ep);   // slot 1: "rank has finished reading the gradients of exchange ep"
+  }
+}
+
+// every peer has finished reading this rank's gradients of the last completed exchange (epoch[0])
+__global__ void __launch_bounds__(32) p2p_wait_done_kernel(int* const* __restrict__ flags, const int* __restrict__ epoch, int rank, int world,
+                                                           int* __restrict__ timed_out) {
+  const int q = threadIdx.x;
+  if (q < world) {
+    const int ep = epoch[0];
+    const int* mine = flags[rank] + kMaxPeers + q;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < ep) {
+      if (clock64() - t0 > 20000000000ll) {
+        atomicExch(timed_out, 1);
+        break;
+      }
+      __nanosleep(40);
+    }
+  }
+}
+
 }  // namespace rc
 
 using namespace rc;
+
+extern "C" int rc_p2p_step(float* param, const float* const* peer_grads, int32_t* const* flags, int32_t* epoch, int rank, int world,
+                           float* exp_avg, float* exp_avg_sq, int64_t* step, long long n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int32_t* timed_out, void* stream) {
+  if (!param || !peer_grads || !flags || !epoch || !exp_avg || !exp_avg_sq || !step || !timed_out || n < 0 || world < 1 ||
+      world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(RC_ERR_ARG, "rc_p2p_step: bad argument (world <= %d)", kMaxPeers);
+  if (n % 4 || !aligned16(param) || !aligned16(exp_avg) || !aligned16(exp_avg_sq))
+    return fail(RC_ERR_ARG, "rc_p2p_step: n must be a multiple of 4 and the buffers 16-byte aligned");
+  long long blocks = ceil_div_ll(n / 4, 256);
+  if (blocks > kNumSMs) blocks = kNumSMs;          // every CTA polls the peers' flags: all of them must be resident
+  if (blocks < 1) blocks = 1;
+  P2pAdamP p;
+  p.grads = peer_grads;
+  p.world = world;
+  p.a = AdamP{param, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<long long*>(step), n, lr, beta1, beta2, eps, weight_decay,
+              1.0f / (float)world};
+  p2p_step_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, reinterpret_cast<int* const*>(flags), epoch, rank, timed_out);
+  return check_launch("p2p_step_kernel");
+}
+
+extern "C" int rc_p2p_wait_done(int32_t* const* flags, const int32_t* epoch, int rank, int world, int32_t* timed_out, void* stream) {
+  if (!flags || !epoch || !timed_out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(RC_ERR_ARG, "rc_p2p_wait_done: bad argument");
+  p2p_wait_done_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<int* const*>(flags), epoch, rank, world, timed_out);
+  return check_launch("p2p_wait_done_kernel");
+}
 
 extern "C" int rc_p2p_barrier(int32_t* const* flags, int32_t* epochs, int rank, int world, int slot, int32_t* timed_out,
                               void* stream) {

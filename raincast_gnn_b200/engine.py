@@ -3,7 +3,8 @@
     H2D batch -> DeepSets -> dim_red -> L x GINE layer -> head -> links+CRPS (value and gradient)
               -> backward of every block -> [sum of the ranks' flat gradients] -> fused AdamW
 
-captured once in a CUDA graph and replayed, with parameters, gradients and Adam moments in flat buffers.
+captured once in a CUDA graph (optimiser and peer-memory gradient exchange included) and replayed, with parameters,
+gradients and Adam moments in flat buffers.
 No autograd, no per-step Python dispatch, no host sync: the loss stays on the device (train.py's per-step
 `loss.item()` becomes one read per epoch).  Data-parallel semantics are DDP's: per-rank BatchNorm
 statistics, per-rank mean over valid nodes, mean of rank gradients.  The 0.84 MB gradient bucket
@@ -158,17 +159,39 @@ class TrainEngine:
                 "layers": layers, "head": (pick(P, hd_map), pick(G, hd_map))}
 
     # ------------------------------------------------------------------ one forward + loss + backward (no optimiser)
+    @property
+    def _opt_in_graph(self) -> bool:
+        """The optimiser (and the peer-memory gradient exchange) is part of the captured step; only the NCCL all-reduce
+        fallback runs eagerly after the replay."""
+        return self.world == 1 or self.p2p is not None
+
     def _fwd_bwd(self):
+        """One whole training step on the current stream (+ the side stream): forward, CRPS, backward and - unless the
+        gradients travel through NCCL - the gradient exchange, AdamW and the running loss sum.  This is what the CUDA
+        graph holds."""
         K.SIDE.stream = self._side
         try:
             self._fwd_bwd_body()
             K.join_side()
         finally:
             K.SIDE.stream = None
+        if self._opt_in_graph:
+            self._optimizer()
+            self.loss_sum.add_(self.loss)
 
     def _fwd_bwd_body(self):
         blk = self._blocks
         Pd, Gd = blk["ds"]
+        done_reading = None
+        if self.p2p is not None:
+            # the peers have finished reading this rank's gradients of the previous step (they may now be overwritten):
+            # waited for on the side stream while the forward runs; the backward below waits for the event
+            P = self.p2p
+            with K.on_side():
+                _lib.check(_lib.lib().rc_p2p_wait_done(P["flags"], P["epochs"].data_ptr(), P["rank"], self.world, P["timed_out"].data_ptr(),
+                                                       torch.cuda.current_stream(self.device).cuda_stream), "rc_p2p_wait_done")
+                done_reading = torch.cuda.Event()
+                done_reading.record(torch.cuda.current_stream(self.device))
         K.dimred_prepack(blk["dr"][0], self.feats, self.x)   # side stream, overlaps the DeepSets kernels
         emb, s_ds = K.deepsets_fwd(Pd, self.ens, bf16=(getattr(self.model.deepset, "compute_dtype", "fp32") == "bf16"))
         Pr, Gr = blk["dr"]
@@ -182,6 +205,8 @@ class TrainEngine:
         raw, s_h = K.head_fwd(Ph, h)
         _, d_raw, _ = K.crps_fwd_bwd(raw, self.y, self.kind, raw_input=True, u=self.u_fixed, xi=self.xi, t=self.t,
                                      loss_out=self.loss)
+        if done_reading is not None:
+            torch.cuda.current_stream(self.device).wait_event(done_reading)
         d = K.head_bwd(Ph, s_h, d_raw, Gh)
         for i in reversed(range(len(blk["layers"]))):
             Pl, Gl = blk["layers"][i]
@@ -191,15 +216,12 @@ class TrainEngine:
 
     def _optimizer(self):
         if self.p2p is not None:
-            # barrier (gradients written) -> sum of the peers' gradients + AdamW in one kernel -> barrier (gradients read)
+            # ONE kernel: wait for every rank's gradients, sum them from peer memory in rank order, AdamW, publish "done reading"
             L, P, st = _lib.lib(), self.p2p, torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(L.rc_p2p_barrier(P["flags"], P["epochs"].data_ptr(), P["rank"], self.world, 0, P["timed_out"].data_ptr(), st),
-                       "rc_p2p_barrier")
-            _lib.check(L.rc_p2p_adamw_step(self.flat_p.data_ptr(), P["grads"], self.world, self.exp_avg.data_ptr(),
-                                           self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.n_params, self.lr,
-                                           self.betas[0], self.betas[1], self.eps, self.weight_decay, st), "rc_p2p_adamw_step")
-            _lib.check(L.rc_p2p_barrier(P["flags"], P["epochs"].data_ptr(), P["rank"], self.world, 1, P["timed_out"].data_ptr(), st),
-                       "rc_p2p_barrier")
+            _lib.check(L.rc_p2p_step(self.flat_p.data_ptr(), P["grads"], P["flags"], P["epochs"].data_ptr(), P["rank"], self.world,
+                                     self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.n_params,
+                                     self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, P["timed_out"].data_ptr(), st),
+                       "rc_p2p_step")
             return
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
@@ -215,6 +237,7 @@ class TrainEngine:
         """Build the step: warm up on a side stream and capture fwd+bwd in a CUDA graph.  BatchNorm running statistics
         and Adam state are restored afterwards, so capture has no training effect."""
         snap = {k: v.clone() for k, v in self.model.state_dict().items()}
+        opt_snap = (self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_count.clone())
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -236,8 +259,14 @@ class TrainEngine:
         with torch.no_grad():
             for k, v in self.model.state_dict().items():
                 v.copy_(snap[k])
+            self.exp_avg.copy_(opt_snap[0])
+            self.exp_avg_sq.copy_(opt_snap[1])
+            self.step_count.copy_(opt_snap[2])       # (the peer-exchange epoch is NOT restored: it advances in lock step on all ranks)
         self.loss_sum.zero_()
         self.flat_g.zero_()
+        if self.p2p is not None:
+            torch.cuda.synchronize(self.device)
+            torch.distributed.barrier(self.pg if self.pg is not None else torch.distributed.group.WORLD)
         return self
 
     # ------------------------------------------------------------------ public
@@ -318,12 +347,15 @@ class TrainEngine:
                 self._flipped = False
         else:
             self._fwd_bwd()
-        self._optimizer()
-        self.loss_sum.add_(self.loss)
+        if not self._opt_in_graph:                    # NCCL fallback: all-reduce + AdamW after the captured fwd / bwd
+            self._optimizer()
+            self.loss_sum.add_(self.loss)
         return self.loss
 
     @property
     def launches_per_step(self) -> int:
         """librc kernel launches per step."""
-        opt = 4 if self.p2p is not None else 2        # barrier, tick, sum + AdamW, barrier  |  tick, AdamW
+        if self._opt_in_graph:                        # AdamW / peer exchange are inside the counted step
+            return int(self.kernels_per_step or 0)
+        opt = 1                                       # AdamW after the NCCL all-reduce
         return int(self.kernels_per_step or 0) + opt

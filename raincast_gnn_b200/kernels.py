@@ -18,8 +18,12 @@ import torch
 
 from . import _lib
 from ._lib import (RC_A_RED, RC_A_ROW, RC_B_COL, RC_B_RED, RC_EPI_BN_RELU_BWD, RC_EPI_BN_STATS, RC_EPI_MASK_POS,
-                   RC_EPI_ADD_RES, RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_OP_AFFINE2, RC_OP_BITMASK, RC_OP_BN_RELU, RC_OP_NONE)
+                   RC_EPI_ADD_RES, RC_EPI_NONE, RC_EPI_RELU, RC_EPI_RELU_RES, RC_OP_AFFINE2, RC_OP_BITMASK, RC_OP_BN_RELU,
+                   RC_OP_GINE_AGGR, RC_OP_NONE)
 
+import os
+
+FUSE_GINE = os.environ.get("RC_FUSE_GINE", "1") != "0"     # 0: separate aggregation kernel (A/B measurements, tests)
 BN_EPS = 1e-5          # torch.nn.BatchNorm1d defaults (models/gnn.py:23)
 BN_MOMENTUM = 0.1
 _SM = 148
@@ -89,19 +93,19 @@ def join_side():
     SIDE.keep.clear()
 
 
-def operand(t, ld, op=RC_OP_NONE, p=(None, None, None, None), aux=None, ld_aux=0, bits=None, ld_bits=0):
+def operand(t, ld, op=RC_OP_NONE, p=(None, None, None, None), aux=None, ld_aux=0, bits=None, ld_bits=0, idx0=None, idx1=None):
     return _lib.rc_operand(_lib.ptr(t), ld, op, _lib.ptr(p[0]), _lib.ptr(p[1]), _lib.ptr(p[2]), _lib.ptr(p[3]),
-                           _lib.ptr(aux), ld_aux, _lib.ptr(bits), ld_bits)
+                           _lib.ptr(aux), ld_aux, _lib.ptr(bits), ld_bits, _lib.ptr(idx0), _lib.ptr(idx1))
 
 
 def gemm(m, n, k, a: _lib.rc_operand, b: _lib.rc_operand, d, ldd, *, a_layout=RC_A_ROW, b_layout=RC_B_COL, bias=None,
          bias_scale=1.0, epi=RC_EPI_NONE, res=None, ld_res=0, bits_out=None, ld_bits_out=0, e_aux=None, ld_e_aux=0,
          e_p=(None, None, None, None), stats=None, splits=1, split_stride=0, colsum_a=None, a2=None, lda2=0, b2=None,
-         ldb2=0, k2=0, rows_per_warp=0, run=True):
+         ldb2=0, k2=0, rows_per_warp=0, a_out=None, ld_a_out=0, run=True):
     g = _lib.rc_gemm(m, n, k, a_layout, b_layout, a, b, _lib.ptr(a2), lda2, _lib.ptr(b2), ldb2, k2, _lib.ptr(d), ldd,
                      _lib.ptr(bias), bias_scale, epi, _lib.ptr(res), ld_res, _lib.ptr(bits_out), ld_bits_out,
                      _lib.ptr(e_aux), ld_e_aux, _lib.ptr(e_p[0]), _lib.ptr(e_p[1]), _lib.ptr(e_p[2]), _lib.ptr(e_p[3]),
-                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp, None, 0)
+                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp, None, 0, _lib.ptr(a_out), ld_a_out)
     if run:
         L = _lib.lib()
         ws_bytes = int(L.rc_gemm_tc_workspace(C.byref(g)))     # > 0: large activation GEMM -> tensor cores (3xTF32)
@@ -382,7 +386,15 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     dev = x.device
     st = _stream(x)
     agg = _new_like(x)
-    gine_aggr_fwd(x, graph, P["lin_w"], P["lin_b"], P["eps"], agg)
+    # small graphs (every reference-shape batch): the aggregation is the operand prologue of the first Linear - one kernel
+    # for message + aggregation + (1+eps) x + Linear1 + BatchNorm tile statistics; large graphs aggregate over station
+    # tiles (shared-memory staging) and run the Linear on the tensor cores
+    fused = FUSE_GINE and m < 16384 and h % 4 == 0 and graph.tiles(h) is None
+    a_op = (operand(x, h, RC_OP_GINE_AGGR, (P["lin_w"], P["lin_b"], P["eps"], None), aux=graph.attr, idx0=graph.rowptr, idx1=graph.col)
+            if fused else operand(agg, h))
+    a_out = agg if fused else None
+    if not fused:
+        gine_aggr_fwd(x, graph, P["lin_w"], P["lin_b"], P["eps"], agg)
     hid = P["nn0_w"].shape[0]
     t = _new((m, hid), torch.float32, dev)
     mean = _new(hid, torch.float32, dev)
@@ -393,12 +405,12 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
         row_tile = gemm_row_tile(m, hid, h)
         tiles = math.ceil(m / row_tile)
         stats = _new((tiles, 2, hid), torch.float32, dev)
-        gemm(m, hid, h, operand(agg, h), operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"], epi=RC_EPI_BN_STATS, stats=stats)
+        gemm(m, hid, h, a_op, operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"], epi=RC_EPI_BN_STATS, stats=stats, a_out=a_out, ld_a_out=h)
         _lib.check(L.rc_bn_stats_finalize(stats.data_ptr(), tiles, row_tile, m, hid, BN_EPS, BN_MOMENTUM, mean.data_ptr(),
                                           rstd.data_ptr(), P["bn_rm"].data_ptr(), P["bn_rv"].data_ptr(),
                                           P["bn_nbt"].data_ptr(), st), "rc_bn_stats_finalize")
     else:
-        gemm(m, hid, h, operand(agg, h), operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"])
+        gemm(m, hid, h, a_op, operand(P["nn0_w"], h), t, hid, bias=P["nn0_b"], a_out=a_out, ld_a_out=h)
         _lib.check(L.rc_bn_eval_prepare(P["bn_rm"].data_ptr(), P["bn_rv"].data_ptr(), hid, BN_EPS, mean.data_ptr(),
                                         rstd.data_ptr(), st), "rc_bn_eval_prepare")
     out_dim = P["nn3_w"].shape[0]

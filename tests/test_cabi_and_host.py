@@ -27,11 +27,19 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().rc_version() == 100
 
 
-def test_struct_sizes_match_header():
-    """ctypes mirrors must have the C layout (64-bit): spot-check sizes against hand-computed values."""
-    assert ctypes.sizeof(_lib.rc_csr) == 80
-    assert ctypes.sizeof(_lib.rc_operand) == 80
-    assert ctypes.sizeof(_lib.rc_reduce_seg) == 48
+def test_struct_sizes_match_header(tmp_path):
+    """ctypes mirrors must have the C layout: sizes and a few field offsets as gcc lays out include/rc_b200.h."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rc_b200.h"\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(rc_csr), sizeof(rc_operand), sizeof(rc_reduce_seg), sizeof(rc_gemm), sizeof(rc_gine_tiles), '
+                   'offsetof(rc_gemm, stats), offsetof(rc_gemm, tc_ws), offsetof(rc_gemm, a_out)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    want = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    got = [ctypes.sizeof(_lib.rc_csr), ctypes.sizeof(_lib.rc_operand), ctypes.sizeof(_lib.rc_reduce_seg), ctypes.sizeof(_lib.rc_gemm),
+           ctypes.sizeof(_lib.rc_gine_tiles), _lib.rc_gemm.stats.offset, _lib.rc_gemm.tc_ws.offset, _lib.rc_gemm.a_out.offset]
+    assert got == want
 
 
 def test_errors_are_reported_not_swallowed():
