@@ -73,7 +73,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -117,12 +117,23 @@ def make_host_batches(n_batches: int, batch: int, seed: int, rank: int, world: i
     return out
 
 
-def static_graph(batch: int):
-    from raincast_gnn_b200 import graph as G
+def static_graph(batch: int, oracle_only: bool = False):
+    """The synthetic reference station graph and its `batch`-fold collation.  oracle_only: built with
+    oracle/graph.py (numpy) so that the CPU arm never loads the repo's native library."""
     from raincast_gnn_b200.utils import synthetic as syn
-    ei, ea = G.radius_graph(syn.distance_matrix(syn.station_coords(N_STATIONS, 600.0, seed=0)), 100.0)
+    dist = syn.distance_matrix(syn.station_coords(N_STATIONS, 600.0, seed=0))
+    if oracle_only:
+        import numpy as np
+        from oracle import graph as og
+        ei, ea = og.radius_graph(np.asarray(dist), 100.0)
+        ei_b, ea_b = og.collate_edges(ei, ea, N_STATIONS, batch)
+        ei, ea, ei_b, ea_b = (torch.as_tensor(t) for t in (ei, ea, ei_b, ea_b))
+        ea, ea_b = ea.reshape(-1, 1), ea_b.reshape(-1, 1)
+    else:
+        from raincast_gnn_b200 import graph as G
+        ei, ea = G.radius_graph(dist, 100.0)
+        ei_b, ea_b = G.collate_static(ei, ea, N_STATIONS, batch)
     assert ei.shape[1] == 1164, "synthetic reference graph must have 1 164 edges (SURVEY.md 8d)"
-    ei_b, ea_b = G.collate_static(ei, ea, N_STATIONS, batch)
     return ei, ea, ei_b, ea_b
 
 
@@ -142,7 +153,7 @@ def cpu_steps_per_second(steps: int, warmup: int, budget_s: float):
     model = seeded_model(om.GNN)
     model.train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
-    ei, ea, ei_b, ea_b = static_graph(B_PER_GPU)
+    ei, ea, ei_b, ea_b = static_graph(B_PER_GPU, oracle_only=True)
     batches = make_host_batches(4, B_PER_GPU, seed=7, rank=0, world=1)
 
     def one(i):
@@ -269,6 +280,163 @@ def measure_deepsets_contraction(dev, peaks, iters: int = 5):
     return out
 
 
+def measure_fp32_peak(dev):
+    """fp32 FMA throughput of this GPU (MEASURED_PEAKS.json has no fp32 figure): 16 independent FFMA chains per thread,
+    8 CTAs of 256 threads per SM; the best of five launches of ~1 ms."""
+    import ctypes as C
+    from raincast_gnn_b200 import _lib
+    L = _lib.lib()
+    scratch = torch.zeros(4, device=dev)
+    flops = C.c_double(0.0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    best = 0.0
+    for _ in range(6):
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(L.rc_debug_fma_peak(scratch.data_ptr(), 2000, C.byref(flops), st), "rc_debug_fma_peak")
+        c.record()
+        c.synchronize()
+        best = max(best, flops.value / (a.elapsed_time(c) * 1e-3) / 1e12)
+    return best
+
+
+def step_flops_bytes():
+    """Algorithmic work of one reference-shape training step (hoisted DeepSets form: the second phi Linear is
+    applied once per station): forward FLOPs x 3 (backward = data + weight gradients), and the compulsory HBM bytes - the
+    batch in, every parameter / gradient / Adam moment once (28 B per parameter), every saved activation written and read once."""
+    m, em, f, h, c, L = B_PER_GPU * N_STATIONS, MEMBERS, FEATS, HIDDEN, 5, LAYERS
+    e = 1164 * B_PER_GPU
+    fwd = 2 * m * em * f * h + 3 * 2 * m * h * h + 2 * m * (f + h) * h + L * (2 * 2 * m * h * h + 3 * e * h) + 2 * m * h * c
+    params = h * f + h + 3 * (h * h + h) + h * (f + h) + h + L * (1 + 2 * h + 2 * (h * h + h) + 2 * h) + c * h + c
+    acts = m * h * (4 + 1 + L * 4)                 # pooled, s2, r1, emb, node; per layer x, agg, t, y
+    bytes_ = 4 * (m * f + m * em * f + m) + 28 * params + 2 * 4 * acts + 2 * 8 * e
+    return 3.0 * fwd, float(bytes_), params
+
+
+def measure_gpu_eager(dev, steps=20, warmup=5):
+    """The oracle's plain PyTorch ops run eagerly on this GPU (library kernels: the only 'existing Blackwell path' the
+    reference has): train steps per second on the benchmark's batch, CUDA events."""
+    from oracle import model as om, pyg as opyg
+    model = seeded_model(om.GNN).to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    ei, ea, ei_b, ea_b = static_graph(B_PER_GPU, oracle_only=True)
+    batches = make_host_batches(2, B_PER_GPU, seed=7, rank=0, world=1)
+    dbs = [opyg.Data(x=x.to(dev), ensemble=en.to(dev), edge_index=ei_b.to(dev), edge_attr=ea_b.to(dev), y=y.to(dev)) for x, en, y in batches]
+
+    def one(i):
+        d = dbs[i % len(dbs)]
+        loss = model.loss_fn.crps(model(d), d.y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize(dev)
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        one(i).item()                                   # train.py:71 reads the loss every step
+    c.record()
+    c.synchronize()
+    ms = a.elapsed_time(c) / steps
+    return {"value": B_PER_GPU / (ms * 1e-3), "unit": "graphs/s", "ms_per_step": ms,
+            "what": "oracle modules (reference arithmetic, PyG GINEConv restatement) in eager PyTorch on this GPU, library kernels, fp32"}
+
+
+def measure_scaled_step(dev, hidden: int, bf16: bool, iters: int = 3):
+    """One whole training step at the config-4 shape (one 100k-node graph, 2 978 560 edges, 51 members): ms per step,
+    CUDA events, kernels issued eagerly (a step of several ms is not launch bound)."""
+    from raincast_gnn_b200 import graph as G
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.utils import synthetic as syn
+    n, em = 100_000, 51
+    ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
+    sg = G.build_station_graph(ei, ea, n).to(dev)
+    x, ens = syn.node_features(n, em, FEATS, seed=3)
+    y = syn.log_precip_targets(n, seed=3)
+    kw = dict(MODEL_KW, hidden_channels_gnn=hidden, out_channels_gnn=hidden)
+    model = GNN(**kw)
+    model.load_state_dict(syn.seeded_state_dict(model.state_dict(), seed=2024))
+    model.to(dev).train()
+    if bf16:
+        model.deepset.compute_dtype = "bf16"
+    eng = TrainEngine(model, sg, n, em, FEATS, use_cuda_graph=False)
+    eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
+    for _ in range(2):
+        eng.step()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        eng.step()
+    c.record()
+    c.synchronize()
+    out = {"ms_per_step": a.elapsed_time(c) / iters, "loss": float(eng.loss.item())}
+    del eng, model, sg
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_train_loop(dev, n_dates: int = 512):
+    """train.py's epoch loop as shipped (run_epoch_engine): DataLoader collate on the host, pinning, the next batch's
+    H2D copy prefetched on a copy stream, one captured step per batch, the ragged last batch stepped eagerly, one loss
+    read per epoch.  graphs/s over one epoch of `n_dates` synthetic dates (wall clock, after a warm-up epoch)."""
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.pyg_compat import DataLoader
+    from raincast_gnn_b200.train import run_epoch_engine
+    from raincast_gnn_b200.utils.dataset import SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=n_dates + 3, members=MEMBERS)       # + 3: the epoch ends on a ragged batch, like the reference's splits
+    loader = DataLoader(ds, batch_size=B_PER_GPU, shuffle=True)
+    first = next(iter(loader))
+    model = seeded_model(GNN).to(dev).train()
+    eng = TrainEngine(model, first.station_graph, first.x.shape[0], MEMBERS, FEATS, lr=1e-4).capture()
+    run_epoch_engine(eng, loader)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    loss = run_epoch_engine(eng, loader)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"value": len(ds) / dt, "unit": "graphs/s", "epoch_s": dt, "dates": len(ds), "mean_loss": loss,
+            "what": "run_epoch_engine over a shuffled DataLoader: host collate + pin + prefetched H2D + captured step; wall clock"}
+
+
+def dp_check(dev, pg, rank, world, steps: int = 4):
+    """Data-parallel correctness carried by the bench line (N > 1): after `steps` steps from one initialisation the
+    replicas are bit-identical (max |difference| of the flat parameters across ranks = 0), and the peer-memory exchange
+    gives the loss trajectory of the NCCL all-reduce (max relative difference)."""
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.graph import build_station_graph
+    from raincast_gnn_b200.models import GNN
+    ei, ea, ei_b, ea_b = static_graph(B_PER_GPU)
+    m = B_PER_GPU * N_STATIONS
+    batches = make_host_batches(steps, B_PER_GPU, seed=11, rank=rank, world=world)
+    out = {}
+    traj = {}
+    for mode in ("p2p", "nccl"):
+        os.environ["RC_DP_EXCHANGE"] = mode
+        model = seeded_model(GNN).to(dev).train()
+        eng = TrainEngine(model, build_station_graph(ei_b, ea_b, m).to(dev), m, MEMBERS, FEATS, lr=1e-3, process_group=pg).capture()
+        ls = []
+        for i in range(steps):
+            eng.load_batch(*batches[i])
+            ls.append(eng.step().clone())
+        torch.cuda.synchronize(dev)
+        traj[mode] = torch.cat(ls)
+        flat = eng.flat_p.detach().clone()
+        lo, hi = flat.clone(), flat.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN, group=pg)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX, group=pg)
+        out[f"replicas_max_abs_diff_{mode}"] = float((hi - lo).abs().max())
+        out[f"exchange_{mode}"] = "peer memory" if eng.p2p is not None else "nccl all-reduce"
+        del eng, model
+    os.environ.pop("RC_DP_EXCHANGE", None)
+    out["replicas_identical"] = out["replicas_max_abs_diff_p2p"] == 0.0 and out["replicas_max_abs_diff_nccl"] == 0.0
+    out["loss_vs_nccl"] = float(((traj["p2p"] - traj["nccl"]).abs() / traj["nccl"].abs()).max())
+    return out
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -354,7 +522,7 @@ def run_b200(args):
             "steps": K_steps, "warmup": W, "ms_per_step": ms_dev / K_steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": (f"dp{world} (dates sharded; per step one exchange of {eng.n_params} fp32 gradients: " +
-                                       ("summed from NVLink peer memory inside the AdamW kernel)" if eng.p2p is not None else "one NCCL all-reduce)"))
+                                       ("waited for, summed from NVLink peer memory and applied by ONE kernel inside the captured step)" if eng.p2p is not None else "one NCCL all-reduce)"))
                                       if world > 1 else "single GPU (dates would be sharded rank::world; no gradient exchange)",
                        "timing": "per-step CUDA events on the launch stream; 256 MiB L2 flush between timed steps, outside the events; max over ranks",
                        "cuda_graph": True, "final_loss": final_loss},
@@ -363,6 +531,11 @@ def run_b200(args):
             "gpu_launches": eng.launches_per_step * K_steps, "launches_per_step": eng.launches_per_step,
             "clocks": clocks.summary(), "wall_s_device_loop": wall_dev}
 
+    if world > 1:
+        try:
+            line["dp_check"] = dp_check(dev, pg, rank, world)
+        except Exception as exc:
+            line["dp_check"] = {"error": repr(exc)}
     if rank == 0:
         peaks, peak_kind = load_peaks()
         if not args.no_roofline:
@@ -394,6 +567,29 @@ def run_b200(args):
                 line["roofline"]["bwd"]["traffic"] = tr.get("gine_aggr_bwd_dram_bytes")
             except OSError:
                 pass
+        if not args.no_roofline:
+            try:
+                fl, by, n_par = step_flops_bytes()
+                fp32_peak = measure_fp32_peak(dev)
+                t_step = ms_dev / K_steps * 1e-3
+                t_floor = max(fl / (fp32_peak * 1e12), by / (peaks["hbm_gbs"] * 1e9))
+                line["step_roofline"] = {"flops_per_step": fl, "bytes_per_step": by, "achieved_tflops": fl / t_step / 1e12,
+                                         "fp32_fma_peak_tflops_measured": fp32_peak, "frac_fp32_peak": fl / t_step / 1e12 / fp32_peak,
+                                         "achieved_gbs": by / t_step / 1e9, "frac_hbm": by / t_step / 1e9 / peaks["hbm_gbs"],
+                                         "floor_us": t_floor * 1e6, "frac_of_floor": t_floor / t_step,
+                                         "note": "the reference-shape step (976 nodes) is bound by neither: it is a chain of ~45 dependent kernels "
+                                                 "of a few microseconds (launch / dependency latency); see config4 for the throughput regime"}
+            except Exception as exc:
+                line["step_roofline"] = {"error": repr(exc)}
+        if world == 1 and not args.no_roofline:
+            for key, fn in (("gpu_eager_baseline", lambda: measure_gpu_eager(dev)),
+                            ("config4", lambda: dict(measure_scaled_step(dev, HIDDEN, False), workload="one 100k-node graph, 2 978 560 edges, 51 members, H=128, L=4, fp32 (3xTF32 tensor cores)")),
+                            ("config5", lambda: dict(measure_scaled_step(dev, 512, True), workload="config-4 graph, bf16 DeepSets (tcgen05 kind::f16), H=512, L=4")),
+                            ("train_loop_e2e", lambda: measure_train_loop(dev))):
+                try:
+                    line[key] = fn()
+                except Exception as exc:            # never lose the bench line over an extra leg
+                    line[key] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             sps, done, dt, cores = cpu_steps_per_second(10_000, 3, budget_s=12.0)
             line["cpu_baseline"] = {"value": sps * B_PER_GPU, "unit": "graphs/s", "cores": cores, "kind": "port",

@@ -264,13 +264,13 @@ int rc_deepsets_pool_fwd(const float* ens, const float* w1, const float* b1, flo
                          int members, int feats, int hidden, void* stream);
 /* Same contraction with bf16 operands and fp32 accumulation on the tensor cores (tcgen05 + TMEM; BASELINE.json
  * config 5).  rc_deepsets_pool_fwd itself switches to the tensor cores with an fp32-accurate 3xTF32 split when
- * num_nodes*members >= 65536 and 128 | hidden (override: RC_DEEPSETS_TC=0/1). */
+ * num_nodes*members >= 8192 and 128 | hidden (override: RC_DEEPSETS_TC=0/1). */
 int rc_deepsets_pool_fwd_bf16(const float* ens, const float* w1, const float* b1, float* pooled, int num_nodes,
                               int members, int feats, int hidden, void* stream);
 /* d w1 / d b1 partials from d pooled (ReLU mask recomputed, nothing saved in forward):
  * partials[nblocks][H*F + H]. */
 int rc_deepsets_pool_bwd_nblocks(int num_nodes, int members, int feats, int hidden);
-/* With num_nodes*members >= 65536 and 11 or 51 members (the reference's ensembles) the backward also runs on the tensor
+/* With num_nodes*members >= 8192 and 11 or 51 members (the reference's ensembles) the backward also runs on the tensor
  * cores (tcgen05, 3xTF32; RC_DEEPSETS_TC=0/1 overrides).  mask_bits_out (nullable, tests): the ReLU mask the backward
  * used, bit (c % 32) of word [row * ceil(H/32) + c / 32] for member row `row`, channel c. */
 int rc_deepsets_pool_bwd(const float* ens, const float* w1, const float* b1, const float* d_pooled,
@@ -358,6 +358,8 @@ int rc_debug_gine_msg_mask(const float* x, const int32_t* t_rowptr, const float*
 /* ReLU behind BatchNorm as the RC_EPI_BN_RELU_BWD epilogue evaluates it: bits_out[m][ceil(n/32)] */
 int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, const float* rstd, const float* gamma, const float* beta,
                           int m, int n, uint32_t* bits_out, void* stream);
+/* fp32 FMA throughput probe (bench.py step_roofline: the measured fp32 peak); *flops = operations one launch executes */
+int rc_debug_fma_peak(float* scratch, int iters, double* flops, void* stream);
 /* tensor-core GEMM timeline of CTA 0 (tools/trace_gemm_tc.py) */
 void rc_debug_tc_trace(void* device_buf);
 /* tensor-core DeepSets pool backward: clocks of CTA 0, int64 [8 events][32 stages] (tools/trace_pool_bwd.py) */

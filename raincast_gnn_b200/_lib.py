@@ -105,6 +105,7 @@ def _declare(lib):
         "rc_p2p_wait_done": (i, [p, p, i, i, p, p]),
         "rc_debug_gine_msg_mask": (i, [p, p, p, p, p, i, i, i, p, p]),
         "rc_debug_bn_relu_mask": (i, [p, i, p, p, p, p, i, i, p, p]),
+        "rc_debug_fma_peak": (i, [p, i, p, p]),
         "rc_debug_tc_trace": (None, [p]),
         "rc_debug_ds_trace": (None, [p]),
     }

@@ -88,3 +88,33 @@ extern "C" int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, 
 }
 
 extern "C" void rc_debug_ds_trace(void* device_buf) { deepsets_bwd_tc_set_trace(static_cast<long long*>(device_buf)); }
+
+// ---------------------------------------------------------------------------------------------- fp32 FMA peak
+// MEASURED_PEAKS.json has HBM and bf16 tensor figures but no fp32 one ("the build must measure one"):
+// 16 independent FMA chains per thread, 8 resident CTAs of 256 threads per SM, `iters` x 16 x 8 FFMA per thread.
+namespace rc {
+__global__ void __launch_bounds__(256) dbg_fma_peak_kernel(float* out, int iters, float a, float b) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += v[i];
+  if (s == 12345.678f) out[0] = s;              // never true: keeps the chains alive
+}
+}  // namespace rc
+
+/* launches the FMA-peak kernel; returns the number of floating-point operations it executes (2 per FMA) in *flops */
+extern "C" int rc_debug_fma_peak(float* scratch, int iters, double* flops, void* stream) {
+  if (!scratch || iters <= 0 || !flops) return fail(RC_ERR_ARG, "rc_debug_fma_peak: bad argument");
+  const int grid = 8 * kNumSMs;
+  dbg_fma_peak_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(scratch, iters, 1.000001f, 1e-7f);
+  *flops = 2.0 * (double)grid * 256.0 * (double)iters * 128.0;
+  return check_launch("dbg_fma_peak_kernel");
+}

@@ -347,7 +347,9 @@ bool deepsets_tc_applicable(int num_nodes, int members, int feats, int hidden) {
   const bool legal = members >= 1 && members <= kTcRows && feats >= 1 && feats <= 64 && hidden >= 1;
   if (!legal || forced == 2) return false;
   if (forced == 1) return true;
-  return (long long)num_nodes * members >= 65536 && hidden % 128 == 0;
+  // from ~8k member rows the tensor-core kernel also wins at the reference shape (8 graphs x 122 stations x 11 members =
+  // 10 736 rows: the training step went from 0.376 to 0.362 ms with both DeepSets kernels on tcgen05)
+  return (long long)num_nodes * members >= 8192 && hidden % 128 == 0;
 }
 
 template <bool BF16, int MEMBERS, int KQ>

@@ -420,7 +420,7 @@ bool deepsets_bwd_tc_applicable(int num_nodes, int members, int feats, int hidde
   const bool legal = (members == 11 || members == 51) && feats >= 1 && feats <= 64 && hidden >= 1;
   if (!legal || forced == 2) return false;
   if (forced == 1) return true;
-  return (long long)num_nodes * members >= 65536;
+  return (long long)num_nodes * members >= 8192;
 }
 
 int deepsets_bwd_tc_blocks(int num_nodes, int members) {

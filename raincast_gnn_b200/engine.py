@@ -352,6 +352,47 @@ class TrainEngine:
             self.loss_sum.add_(self.loss)
         return self.loss
 
+    def step_eager(self, x, ensemble, y, graph: StationGraph):
+        """One training step on a batch of a DIFFERENT size than the captured one (the ragged last batch of an epoch,
+        train.py:61-71): the same kernel schedule issued eagerly on `graph` / the given device tensors."""
+        keep = (self.x, self.ens, self.y, self.graph, self.m)
+        self.x, self.ens, self.y = (_lib.f32c(t) for t in (x, ensemble, y.reshape(-1)))
+        self.graph, self.m = graph.to(self.device), int(x.shape[0])
+        try:
+            self._fwd_bwd()
+            if not self._opt_in_graph:
+                self._optimizer()
+                self.loss_sum.add_(self.loss)
+        finally:
+            self.x, self.ens, self.y, self.graph, self.m = keep
+        return self.loss
+
+    def step_emulated_ranks(self, batches):
+        """One data-parallel step of G = len(batches) ranks emulated on ONE GPU (never spin-wait across
+        ranks on one device): every micro-batch runs forward / CRPS / backward with its own BatchNorm statistics and its
+        own valid-node mean, the G flat gradients are summed in rank order, and ONE AdamW step takes their mean
+        (grad_scale = 1/G) - the arithmetic of rc_p2p_step / all-reduce + rc_adamw_step.  Returns the G losses and the
+        mean gradients by parameter name."""
+        total = torch.zeros_like(self.flat_g)
+        losses = []
+        for x, ens, y in batches:
+            self.load_batch(x, ens, y)
+            K.SIDE.stream = self._side
+            try:
+                self._fwd_bwd_body()
+                K.join_side()
+            finally:
+                K.SIDE.stream = None
+            total += self.flat_g
+            losses.append(self.loss.clone())
+        _lib.check(_lib.lib().rc_adamw_step(self.flat_p.data_ptr(), total.data_ptr(), self.exp_avg.data_ptr(),
+                                            self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.n_params, self.lr,
+                                            self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / len(batches),
+                                            torch.cuda.current_stream(self.device).cuda_stream), "rc_adamw_step")
+        mean = total / len(batches)
+        grads = {k: mean[v.data_ptr() // 4 - self.flat_g.data_ptr() // 4:][:v.numel()].view(v.shape).clone() for k, v in self.grads.items()}
+        return torch.cat(losses), grads
+
     @property
     def launches_per_step(self) -> int:
         """librc kernel launches per step."""

@@ -43,7 +43,10 @@ def parse_args(argv=None):
                      ("--synthetic", dict(type=int, default=0, help="number of synthetic dates (0: EUPPBench files)")),
                      ("--max_epochs", dict(type=int, default=None))):
         ap.add_argument(flag, **kw)
-    ap.add_argument("--engine", action="store_true", help="CUDA-graph training engine instead of autograd")
+    ap.add_argument("--engine", action="store_true", default=True,
+                    help="CUDA-graph training engine: the explicit kernel schedule of one train.py iteration, fused AdamW (default)")
+    ap.add_argument("--autograd", dest="engine", action="store_false",
+                    help="the reference's loop verbatim: module forward, loss.backward() through torch.autograd, torch.optim.AdamW")
     ap.add_argument("--resident", action="store_true",
                     help="with --engine: keep the training split on the GPU and build batches there (no per-step collate / H2D)")
     return ap.parse_args(argv)
@@ -85,7 +88,15 @@ def run_epoch_engine(engine: TrainEngine, loader) -> float:
     engine.loss_sum.zero_()
     done = 0
     pinned = torch.cuda.is_available()
-    it = (b for b in loader if b.x.shape[0] == engine.m)   # the captured step has a fixed shape: a ragged last batch is skipped
+    ragged = []                                            # the last batch of an epoch may be smaller (train.py:61-71 trains on it)
+
+    def full_batches():
+        for b in loader:
+            if b.x.shape[0] == engine.m:
+                yield b
+            else:
+                ragged.append(b)
+    it = full_batches()
 
     def start(batch):
         host = [t.pin_memory() if pinned and t.device.type == "cpu" and not t.is_pinned() else t for t in (batch.x, batch.ensemble, batch.y)]
@@ -101,6 +112,10 @@ def run_epoch_engine(engine: TrainEngine, loader) -> float:
         held = nxt
         done += 1
     del held
+    for b in ragged:                                       # same kernels, stepped outside the captured graph (once per epoch)
+        b = b.to(engine.device)
+        engine.step_eager(b.x, b.ensemble, b.y, b.station_graph)
+        done += 1
     return engine.loss_sum.item() / max(done, 1)
 
 
@@ -109,8 +124,16 @@ def run_epoch_resident(engine: TrainEngine, split: DeviceSplit, batch_size: int,
     engine.loss_sum.zero_()
     batches = split.epoch_batches(batch_size, generator=generator)
     for dates in batches:
-        engine.load_dates(split, dates)
-        engine.step()
+        if int(dates.numel()) * split.num_stations == engine.m:
+            engine.load_dates(split, dates)
+            engine.step()
+        else:                                              # ragged last batch
+            from .graph import build_station_graph, collate_static
+            b = int(dates.numel())
+            ei, ea = collate_static(split.edge_index, split.edge_attr, split.num_stations, b)
+            g = build_station_graph(ei, ea, b * split.num_stations).to(engine.device)
+            engine.step_eager(split.x[dates].reshape(-1, split.x.shape[-1]), split.ensemble[dates].reshape(-1, *split.ensemble.shape[2:]),
+                              split.y[dates].reshape(-1), g)
     return engine.loss_sum.item() / max(len(batches), 1)
 
 
@@ -171,7 +194,7 @@ def main(argv=None):
         engine = TrainEngine(model, first.station_graph, first.x.shape[0], first.ensemble.shape[1], first.x.shape[1],
                              lr=cfg["lr"], process_group=group).capture()
     elif world > 1:
-        raise SystemExit("data-parallel training needs --engine (the gradient all-reduce lives in the engine)")
+        raise SystemExit("data-parallel training needs the engine (the gradient exchange lives there): drop --autograd")
     else:
         optimizer = model.optimizer_class(model.parameters(), **model.optimizer_params)
 

@@ -48,12 +48,15 @@ class EUPPBench:
                 f"{path} not found. Processing raw EUPPBench Zarr archives (utils/dataset.py:95-182) needs network "
                 "access and xarray/zarr/geopy, which this build does not have; use SyntheticEUPPBench or copy the "
                 "reference's processed .pt files here.")
-        data, slices = torch.load(path, weights_only=False)
+        from ..pyg_compat import unpickle                            # the file names torch_geometric classes: read as attribute bags
+        data, slices = torch.load(path, weights_only=False, pickle_module=unpickle)
         self.graphs = self._unpack(data, slices)
 
     @staticmethod
     def _unpack(data, slices) -> List[Data]:
-        get = (lambda k: data[k]) if isinstance(data, dict) else (lambda k: getattr(data, k))
+        from ..pyg_compat import unpickle
+        attrs = unpickle.attribute_dict(data)
+        get = lambda k: attrs[k]                                     # noqa: E731
         n = len(slices["x"]) - 1
         e0, e1 = int(slices["edge_index"][0]), int(slices["edge_index"][1])
         edge_index = get("edge_index")[:, e0:e1].contiguous()       # static graph: share the first copy
@@ -96,9 +99,8 @@ class DeviceSplit:
         return self.x.shape[0]
 
     def epoch_batches(self, batch_size: int, generator=None, shuffle: bool = True):
-        """Device int64 index tensors of `batch_size` dates each (a ragged last batch is dropped: the captured step has
-        a fixed shape)."""
+        """Device int64 index tensors of `batch_size` dates each; like the reference's DataLoader (train.py:155) the last
+        batch is ragged when the split does not divide (the engine steps it outside the captured graph)."""
         n = len(self)
         order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
-        order = order[: (n // batch_size) * batch_size].to(self.x.device)
-        return list(order.split(batch_size))
+        return list(order.to(self.x.device).split(batch_size))

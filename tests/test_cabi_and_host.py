@@ -288,7 +288,8 @@ def test_station_tiles_verifier_rejects_corruption():
 
 
 def test_device_split_epoch_batches():
-    """DeviceSplit (utils/dataset.py) on the CPU: stacking, fixed-shape batches, ragged tail dropped, reproducible order."""
+    """DeviceSplit (utils/dataset.py) on the CPU: stacking, batches like the reference's DataLoader (ragged last batch kept,
+    train.py:155), reproducible order."""
     from raincast_gnn_b200.utils.dataset import DeviceSplit, SyntheticEUPPBench
     ds = SyntheticEUPPBench(n_dates=11, num_stations=7, members=3, feats=5)
     split = DeviceSplit([ds[i] for i in range(len(ds))], "cpu")
@@ -296,9 +297,62 @@ def test_device_split_epoch_batches():
     assert torch.equal(split.x[4], ds[4].x) and torch.equal(split.ensemble[9], ds[9].ensemble)
     b1 = split.epoch_batches(4, generator=torch.Generator().manual_seed(3))
     b2 = split.epoch_batches(4, generator=torch.Generator().manual_seed(3))
-    assert len(b1) == 2 and all(b.numel() == 4 and b.dtype == torch.int64 for b in b1)
+    assert [b.numel() for b in b1] == [4, 4, 3] and all(b.dtype == torch.int64 for b in b1)
     assert all(torch.equal(a, b) for a, b in zip(b1, b2))
-    assert len(set(torch.cat(b1).tolist())) == 8
-    assert torch.equal(torch.cat(split.epoch_batches(5, shuffle=False)), torch.arange(10))
+    assert sorted(torch.cat(b1).tolist()) == list(range(11))
+    assert torch.equal(torch.cat(split.epoch_batches(5, shuffle=False)), torch.arange(11))
     with pytest.raises(ValueError):
         DeviceSplit([], "cpu")
+
+
+def test_euppbench_reads_reference_processed_file_without_pyg(tmp_path):
+    """utils/dataset.py:174-182 writes torch.save((data, slices)) with `data` a pickled torch_geometric Data (its
+    attributes live in data._store._mapping, PyG 2.x) and utils/dataset.py:57-60 reads it back.  torch-geometric is not
+    installable here: EUPPBench must read such a file with the PyG classes replaced by attribute bags.  The file is
+    written here through stand-in classes registered under PyG's module paths, which are removed again before loading."""
+    import sys
+    import types
+    from raincast_gnn_b200.utils.dataset import EUPPBench, SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=5, num_stations=17, members=3, feats=6, max_dist=250.0)
+    mods = {}
+    for name in ("torch_geometric", "torch_geometric.data", "torch_geometric.data.data", "torch_geometric.data.storage"):
+        mods[name] = types.ModuleType(name)
+
+    class GlobalStorage:                                   # torch_geometric.data.storage.GlobalStorage: attributes in _mapping
+        def __init__(self, mapping, parent):
+            self._mapping, self._parent = mapping, parent
+
+    class Data:                                            # torch_geometric.data.data.Data: one GlobalStorage in _store
+        def __init__(self, mapping):
+            self.__dict__["_store"] = GlobalStorage(mapping, self)
+    GlobalStorage.__module__, GlobalStorage.__qualname__ = "torch_geometric.data.storage", "GlobalStorage"
+    Data.__module__, Data.__qualname__ = "torch_geometric.data.data", "Data"
+    mods["torch_geometric.data.storage"].GlobalStorage = GlobalStorage
+    mods["torch_geometric.data.data"].Data = Data
+    graphs = [ds[i] for i in range(len(ds))]
+    e = graphs[0].edge_index.shape[1]
+    n = graphs[0].x.shape[0]
+    mapping = {"x": torch.cat([g.x for g in graphs]), "ensemble": torch.cat([g.ensemble for g in graphs]),
+               "y": torch.cat([g.y for g in graphs]), "edge_index": torch.cat([g.edge_index for g in graphs], dim=1),
+               "edge_attr": torch.cat([g.edge_attr for g in graphs])}
+    k = len(graphs)
+    slices = {"x": torch.arange(k + 1) * n, "ensemble": torch.arange(k + 1) * n, "y": torch.arange(k + 1) * n,
+              "edge_index": torch.arange(k + 1) * e, "edge_attr": torch.arange(k + 1) * e}
+    path = tmp_path / "EUPPBench_24h_train_rf.pt"
+    sys.modules.update(mods)
+    try:
+        torch.save((Data(mapping), slices), path)
+    finally:
+        for name in mods:
+            sys.modules.pop(name, None)
+    assert "torch_geometric" not in sys.modules
+    got = EUPPBench(root_raw=str(tmp_path), root_processed=str(tmp_path), leadtime="24h", max_dist=250.0, split="train_rf")
+    assert len(got) == k
+    for i in range(k):
+        for key in ("x", "ensemble", "y", "edge_index", "edge_attr"):
+            a, b = getattr(got[i], key), getattr(graphs[i], key)
+            assert torch.equal(torch.nan_to_num(a.reshape(b.shape), nan=-77.0), torch.nan_to_num(b, nan=-77.0)), (i, key)   # (y holds NaN)
+    with pytest.raises(ValueError):
+        EUPPBench(str(tmp_path), str(tmp_path), "24h", 100.0, split="nope")              # utils/dataset.py:52-53
+    with pytest.raises(FileNotFoundError):
+        EUPPBench(str(tmp_path), str(tmp_path), "72h", 100.0, split="train_rf")
