@@ -362,6 +362,8 @@ int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, const float
 int rc_debug_fma_peak(float* scratch, int iters, double* flops, void* stream);
 /* tensor-core GEMM timeline of CTA 0 (tools/trace_gemm_tc.py) */
 void rc_debug_tc_trace(void* device_buf);
+/* rc_p2p_step: globaltimer (ns) of CTA 0 at entry, flags published, all ranks arrived, update done, exit: int64[5] */
+void rc_debug_p2p_trace(void* device_buf);
 /* tensor-core DeepSets pool backward: clocks of CTA 0, int64 [8 events][32 stages] (tools/trace_pool_bwd.py) */
 void rc_debug_ds_trace(void* device_buf);
 

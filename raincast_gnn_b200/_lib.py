@@ -107,6 +107,7 @@ def _declare(lib):
         "rc_debug_bn_relu_mask": (i, [p, i, p, p, p, p, i, i, p, p]),
         "rc_debug_fma_peak": (i, [p, i, p, p]),
         "rc_debug_tc_trace": (None, [p]),
+        "rc_debug_p2p_trace": (None, [p]),
         "rc_debug_ds_trace": (None, [p]),
     }
     for name, (res, args) in sig.items():

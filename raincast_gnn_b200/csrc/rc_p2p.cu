@@ -105,10 +105,18 @@ __global__ void __launch_bounds__(256) p2p_adamw_kernel(const P2pAdamP p) {
 // side stream - it is over long before that step's backward writes its first gradient, i.e. off the critical path.
 // Replaces barrier -> tick -> sum + AdamW -> barrier (four dependent launches after backward).
 static __device__ unsigned int g_p2p_arrivals = 0;
+static long long* g_p2p_trace = nullptr;          // debug (rc_debug_p2p_trace): globaltimer (ns) at the phases of CTA 0
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 __global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* const* __restrict__ flags, int* __restrict__ epoch,
-                                                       int rank, int* __restrict__ timed_out) {
+                                                       int rank, int* __restrict__ timed_out, long long* __restrict__ trace) {
   const AdamP& a = p.a;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) trace[0] = globaltimer_ns();
   __shared__ float s_step_size, s_bc2_sqrt;
   const int ep = epoch[0] + 1;                     // (advanced only by the last CTA to finish)
   if (threadIdx.x < p.world) {
@@ -116,6 +124,7 @@ __global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* co
     if (blockIdx.x == 0) {
       __threadfence_system();                      // this device's earlier kernels' gradient writes, system wide
       st_release_sys(flags[q] + rank, ep);         // slot 0 of rank q's block: "rank's gradients of exchange ep are in place"
+      if (tr) trace[1] = globaltimer_ns();
     }
     const int* mine = flags[rank] + q;
     const long long t0 = clock64();
@@ -134,6 +143,7 @@ __global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* co
     s_bc2_sqrt = (float)sqrt(bc2);
   }
   __syncthreads();
+  if (tr) trace[2] = globaltimer_ns();
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const float decay = 1.0f - a.lr * a.weight_decay, one_m_b1 = 1.0f - a.beta1, one_m_b2 = 1.0f - a.beta2;
   const long long n4 = a.n / 4;
@@ -160,6 +170,7 @@ __global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* co
     reinterpret_cast<float4*>(a.exp_avg_sq)[i] = v2;
   }
   __syncthreads();
+  if (tr) trace[3] = globaltimer_ns();
   __shared__ int s_last;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* co
     __threadfence_system();
     st_release_sys(flags[threadIdx.x] + kMaxPeers + rank, ep);   // slot 1: "rank has finished reading the gradients of exchange ep"
   }
+  if (tr) trace[4] = globaltimer_ns();
 }
 
 // every peer has finished reading this rank's gradients of the last completed exchange (epoch[0])
@@ -216,9 +228,12 @@ extern "C" int rc_p2p_step(float* param, const float* const* peer_grads, int32_t
   p.world = world;
   p.a = AdamP{param, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<long long*>(step), n, lr, beta1, beta2, eps, weight_decay,
               1.0f / (float)world};
-  p2p_step_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, reinterpret_cast<int* const*>(flags), epoch, rank, timed_out);
+  p2p_step_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, reinterpret_cast<int* const*>(flags), epoch, rank, timed_out,
+                                                                                 g_p2p_trace);
   return check_launch("p2p_step_kernel");
 }
+
+extern "C" void rc_debug_p2p_trace(void* device_buf) { g_p2p_trace = static_cast<long long*>(device_buf); }
 
 extern "C" int rc_p2p_wait_done(int32_t* const* flags, const int32_t* epoch, int rank, int world, int32_t* timed_out, void* stream) {
   if (!flags || !epoch || !timed_out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)

@@ -84,6 +84,8 @@ def test_data_parallel_semantics_on_one_gpu_vs_micro_batch_oracle():
         assert (mean_grads[k].cpu().double() - p.grad).abs().max().item() < 1e-5 * max(scale, 1e-12), k
     opt.step()
     for k, p in named.items():                          # and the AdamW step it feeds (first step: ~lr * sign(grad) per entry;
-        got = dict(ours.named_parameters())[k].detach().cpu().double()          #  entries whose gradient is ~eps are ill-conditioned)
+        if k.endswith(".nn.0.bias"):                    #  entries whose gradient is ~eps are ill-conditioned; the bias in front of
+            continue                                    #  BatchNorm has a zero true gradient: Adam normalises pure rounding noise)
+        got = dict(ours.named_parameters())[k].detach().cpu().double()
         firm = p.grad.abs() > 1e-4 * p.grad.abs().max()
         assert ((got - p.detach()).abs() * firm).max().item() < 1e-5 * max(p.detach().abs().max().item(), 1e-3), k
