@@ -217,7 +217,9 @@ typedef struct rc_gemm {
    * call), and for weight-gradient GEMMs (A stored [r][i], B stored [r][j]) with k >= 16384 samples (no workspace).
    * RC_GEMM_TC=0 in the environment keeps everything on the SIMT kernels. */
   void* tc_ws; size_t tc_ws_bytes;
-  float* a_out; int ld_a_out;   /* RC_OP_GINE_AGGR: the A operand after its prologue, written once (nullable) */
+  float* a_out; int ld_a_out;   /* the A operand after its prologue, written once (nullable): RC_OP_GINE_AGGR on the SIMT
+                                   path, every prologue on the tensor-core activation path (the layer's weight-gradient
+                                   GEMM then takes it as a plain operand) */
 } rc_gemm;
 
 int rc_gemm_row_tile(const rc_gemm* g);  /* the row tile the launch would use (for stats sizing)   */

@@ -142,7 +142,7 @@ struct TcRowsP {
   rc_gemm g;
   const float* wpack;
   int kb1, kblocks, n_tiles, row_tiles;
-  int a_vec, a2_vec;
+  int a_vec, a2_vec, a_out_vec;
   int chain;                 // k-blocks per accumulator: 2, or 4 when K > 256 (at most four accumulators per tile)
   long long* trace;          // debug (rc_debug_tc_trace): CTA 0 records [role][tile][begin, end] clocks; NULL in production
   int dbg;                   // debug (RC_TC_DBG): 2 = one accumulator set (no MMA / epilogue overlap)
@@ -294,6 +294,21 @@ __device__ __forceinline__ void tc_rows_producer(const TcRowsP& p, const TcSmem&
       split_tf32_rn(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
       st4(bh + sidx_f(it), hi);
       st4(bl + sidx_f(it), lo);
+      // the operand after its prologue, once (first column tile): the weight-gradient GEMM of the same layer then reads it
+      // as a plain operand instead of re-deriving it element by element (bit mask, BatchNorm backward, ...)
+      if (OP != RC_OP_NONE && g.a_out != nullptr && cu.nt == 0 && cu.kb < p.kb1) {
+        const int row = cu.row0 + rofs_f(it), col = k0 + kofs_t;
+        if (row < g.m) {
+          float* dst = g.a_out + (size_t)row * g.ld_a_out + col;
+          if (col + 3 < g.k && p.a_out_vec) {
+            st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < g.k) dst[e] = v[e];
+          }
+        }
+      }
     }
     fence_async_smem();
     __syncwarp();
@@ -881,6 +896,7 @@ int gemm_tc_run(const rc_gemm* g, cudaStream_t s) {
     p.a_vec = vec_ok(g->a.ptr, g->a.ld);
     if (g->a.op == RC_OP_AFFINE2) p.a_vec = p.a_vec && vec_ok(g->a.aux, g->a.ld_aux);
     p.a2_vec = g->k2 > 0 ? vec_ok(g->a2, g->lda2) : 0;
+    p.a_out_vec = g->a_out ? vec_ok(g->a_out, g->ld_a_out) : 0;
     p.trace = g_tc_trace;
     p.dbg = getenv("RC_TC_DBG") ? atoi(getenv("RC_TC_DBG")) : 0;
     p.wpack = nullptr;

@@ -23,6 +23,7 @@ from ._lib import (RC_A_RED, RC_A_ROW, RC_B_COL, RC_B_RED, RC_EPI_BN_RELU_BWD, R
 
 import os
 
+SAVE_OPERANDS = os.environ.get("RC_SAVE_OPERANDS", "1") != "0"   # large graphs: transformed GEMM operands written out once
 FUSE_GINE = os.environ.get("RC_FUSE_GINE", "1") != "0"     # 0: separate aggregation kernel (A/B measurements, tests)
 BN_EPS = 1e-5          # torch.nn.BatchNorm1d defaults (models/gnn.py:23)
 BN_MOMENTUM = 0.1
@@ -417,14 +418,17 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     y = _new((m, out_dim), torch.float32, dev)
     words = math.ceil(out_dim / 32)
     bits = _new((m, words), torch.int32, dev)
+    # large graphs (tensor-core Linear layers): u = relu(BN(t)) is written out by the GEMM's operand producer and the
+    # backward's weight-gradient GEMM reads it back instead of recomputing it element by element
+    u = _new((m, hid), torch.float32, dev) if (training and SAVE_OPERANDS and gemm_row_tile(m, out_dim, hid) == 64) else None
     gemm(m, out_dim, hid, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), operand(P["nn3_w"], hid),
          y, out_dim, bias=P["nn3_b"], epi=RC_EPI_RELU if first else RC_EPI_RELU_RES, res=None if first else x,
-         ld_res=h, bits_out=bits, ld_bits_out=words)
-    return y, (x, agg, t, mean, rstd, bits)
+         ld_res=h, bits_out=bits, ld_bits_out=words, a_out=u, ld_a_out=hid)
+    return y, (x, agg, t, mean, rstd, bits, u)
 
 
 def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True, need_dx: bool = True):
-    x, agg, t, mean, rstd, bits = saved
+    x, agg, t, mean, rstd, bits, u = saved
     L = _lib.lib()
     m, h = x.shape
     hid = P["nn0_w"].shape[0]
@@ -434,17 +438,23 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     st = _stream(x)
     sink = GradSink(dev)
     do_op = operand(dy, out_dim, RC_OP_BITMASK, bits=bits, ld_bits=words)           # d o = dy * 1[o > 0]
-    # Linear2: d W2 = d o^T u,  u = relu(BN(t)) recomputed in the prologue
-    with on_side(dy):
-        linear_bwd_weight(do_op, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), m, out_dim, hid,
-                          G["nn3_w"], G["nn3_b"], sink)
-    # d z = (d o @ W2) * 1[BN(t) > 0], with the two BatchNorm column reductions in the epilogue
     row_tile = gemm_row_tile(m, hid, out_dim)
+    big = u is not None and row_tile == 64          # tensor-core path: the activation GEMMs write their transformed operand out
+    # Linear2: d W2 = d o^T u,  u = relu(BN(t)) recomputed in the prologue (small graphs) or saved by the forward (large)
+    if not big:
+        with on_side(dy):
+            linear_bwd_weight(do_op, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), m, out_dim, hid,
+                              G["nn3_w"], G["nn3_b"], sink)
+    # d z = (d o @ W2) * 1[BN(t) > 0], with the two BatchNorm column reductions in the epilogue
     tiles = math.ceil(m / row_tile)
     stats = _new((tiles, 2, hid), torch.float32, dev)
     dz = _new((m, hid), torch.float32, dev)
+    do_buf = _new((m, out_dim), torch.float32, dev) if big else None
     gemm(m, hid, out_dim, do_op, operand(P["nn3_w"], hid), dz, hid, b_layout=RC_B_RED, epi=RC_EPI_BN_RELU_BWD, e_aux=t,
-         ld_e_aux=hid, e_p=(mean, rstd, P["bn_w"], P["bn_b"]), stats=stats)
+         ld_e_aux=hid, e_p=(mean, rstd, P["bn_w"], P["bn_b"]), stats=stats, a_out=do_buf, ld_a_out=out_dim)
+    if big:
+        with on_side(do_buf, u):
+            linear_bwd_weight(operand(do_buf, out_dim), operand(u, hid), m, out_dim, hid, G["nn3_w"], G["nn3_b"], sink)
     c0 = _new(hid, torch.float32, dev)
     c1 = _new_like(c0)
     c2 = _new_like(c0)
@@ -452,11 +462,18 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
                                     G["bn_w"].data_ptr(), G["bn_b"].data_ptr(), c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), st),
                "rc_bn_bwd_finalize")
     dt_op = operand(dz, hid, RC_OP_AFFINE2, (c0, c1, c2, mean), aux=t, ld_aux=hid)  # d t = c0*dz + c1*(t-mean) + c2
-    with on_side(dz, c0, c1, c2):
-        linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
-        sink.flush()
     d_agg = _new((m, h), torch.float32, dev)
-    gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
+    if big:
+        dt_buf = _new((m, hid), torch.float32, dev)
+        gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED, a_out=dt_buf, ld_a_out=hid)
+        with on_side(dt_buf):
+            linear_bwd_weight(operand(dt_buf, hid), operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
+            sink.flush()
+    else:
+        with on_side(dz, c0, c1, c2):
+            linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
+            sink.flush()
+        gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
     # aggregation backward (+ residual branch of layers > 0)
     dx = _new((m, h), torch.float32, dev)
     if MASKS.active is not None:

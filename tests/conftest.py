@@ -47,4 +47,16 @@ def grad_scale(key, want_max, lookup_max):
     is rounding noise (~1e-9); it is compared on the scale of its weight's gradient instead."""
     if key.endswith(".nn.0.bias"):
         return max(lookup_max(key[:-4] + "weight"), 1e-12)
+    if key.endswith(".eps") and ".convolutions." in key:
+        # d eps_l = <d h_l, x_l> is ONE scalar per layer, a cancelling inner product over M*H terms: at the reference
+        # shape (11 members, layer 0) it is 4.4e-5 against sum |d h * x| = 0.39, so 1e-5 of its own magnitude would be
+        # 1e-9 of the terms it sums - below what fp32 inputs carry.  The L scalars are compared as one vector.
+        head, _, _ = key.rpartition(".convolutions.")
+        peers = []
+        for layer in range(64):
+            try:
+                peers.append(lookup_max(f"{head}.convolutions.{layer}.eps"))
+            except KeyError:
+                break
+        return max(max(peers, default=want_max), want_max, 1e-12)
     return max(want_max, 1e-12)

@@ -12,11 +12,18 @@ from raincast_gnn_b200.utils import synthetic as syn
 dev = torch.device("cuda:0")
 n, em = 100_000, int(sys.argv[1]) if len(sys.argv) > 1 else 51
 check = len(sys.argv) > 2 and sys.argv[2] == "check"
+hidden = int(sys.argv[3]) if len(sys.argv) > 3 else 128          # 512 + "bf16" as 5th argument: config 5 at this shape
+bf16 = len(sys.argv) > 4 and sys.argv[4] == "bf16"
 ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
 sg = G.build_station_graph(ei, ea, n).to(dev)
 x, ens = syn.node_features(n, em, B.FEATS, seed=3)
 y = syn.log_precip_targets(n, seed=3)
-model = B.seeded_model(GNN).to(dev).train()
+kw = dict(B.MODEL_KW, hidden_channels_gnn=hidden, out_channels_gnn=hidden)
+model = GNN(**kw)
+model.load_state_dict(syn.seeded_state_dict(model.state_dict(), seed=2024))
+model = model.to(dev).train()
+if bf16:
+    model.deepset.compute_dtype = "bf16"
 eng = TrainEngine(model, sg, n, em, B.FEATS, use_cuda_graph=False)
 eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
 blk = eng._blocks
@@ -26,7 +33,7 @@ def ev():
 
 for it in range(3):
     t = [("start", ev())]
-    emb, s_ds = K.deepsets_fwd(blk["ds"][0], eng.ens); t.append(("deepsets fwd", ev()))
+    emb, s_ds = K.deepsets_fwd(blk["ds"][0], eng.ens, bf16=bf16); t.append(("deepsets fwd", ev()))
     node, s_dr = K.dimred_fwd(blk["dr"][0], eng.x, emb); t.append(("dim_red fwd", ev()))
     saved, h = [], node
     for i, (Pl, _) in enumerate(blk["layers"]):
