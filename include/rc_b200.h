@@ -220,6 +220,9 @@ typedef struct rc_gemm {
   float* a_out; int ld_a_out;   /* the A operand after its prologue, written once (nullable): RC_OP_GINE_AGGR on the SIMT
                                    path, every prologue on the tensor-core activation path (the layer's weight-gradient
                                    GEMM then takes it as a plain operand) */
+  int b_static;                 /* 1: the B operand is a parameter - the kernel launched just before this one on the stream
+                                   does not write it.  The kernel then fetches its first B tile BEFORE waiting for that
+                                   kernel (programmatic dependent launch), overlapping the fetch with its tail */
 } rc_gemm;
 
 int rc_gemm_row_tile(const rc_gemm* g);  /* the row tile the launch would use (for stats sizing)   */

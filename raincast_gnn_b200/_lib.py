@@ -47,7 +47,7 @@ class rc_gemm(C.Structure):
                 ("res", _fp), ("ld_res", C.c_int), ("bits_out", _fp), ("ld_bits_out", C.c_int),
                 ("e_aux", _fp), ("ld_e_aux", C.c_int), ("e_p0", _fp), ("e_p1", _fp), ("e_p2", _fp), ("e_p3", _fp),
                 ("stats", _fp), ("splits", C.c_int), ("split_stride", C.c_longlong), ("colsum_a", _fp),
-                ("rows_per_warp", C.c_int), ("tc_ws", _fp), ("tc_ws_bytes", C.c_size_t), ("a_out", _fp), ("ld_a_out", C.c_int)]
+                ("rows_per_warp", C.c_int), ("tc_ws", _fp), ("tc_ws_bytes", C.c_size_t), ("a_out", _fp), ("ld_a_out", C.c_int), ("b_static", C.c_int)]
 
 
 class rc_reduce_seg(C.Structure):

@@ -16,9 +16,8 @@ namespace rc {
 
 template <int RM, int AL, int BL, int kRK>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmP p) {
-  pdl_entry();
   extern __shared__ __align__(16) float smem[];
-  gemm_tile<RM, AL, BL, kRK>(p, blockIdx, smem);
+  gemm_tile<RM, AL, BL, kRK>(p, blockIdx, smem);       // (waits for the kernel before it inside: after the early B fetch)
 }
 
 // `stages`: 2 when a CTA walks more than one reduction slice (double buffering), else 1.  The single-slice GEMMs of
@@ -151,6 +150,8 @@ extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
   const int rk = choose_rk(g, rm);
   p.tiles1 = ceil_div(g->k, rk);
   p.tiles2 = g->k2 > 0 ? ceil_div(g->k2, rk) : 0;
+  static const bool early_ok = !(getenv("RC_GEMM_B_EARLY") && getenv("RC_GEMM_B_EARLY")[0] == '0');   // A/B switch
+  p.b_early = (early_ok && g->b_static && g->b.op == RC_OP_NONE) ? 1 : 0;
   dim3 grid(ceil_div(g->m, 8 * rm), ceil_div(g->n, kBN), g->splits > 1 ? g->splits : 1);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g->a_layout == RC_A_ROW && g->b_layout == RC_B_COL) return gemm_dispatch_rm<RC_A_ROW, RC_B_COL>(rm, rk, p, grid, s);

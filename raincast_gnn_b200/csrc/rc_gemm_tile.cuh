@@ -14,6 +14,7 @@ struct GemmP {
   rc_gemm g;
   int a_vec, b_vec, a2_vec, b2_vec, d_vec;   // 128-bit access allowed (ld % 4 == 0 and 16-byte aligned base)
   int tiles1, tiles2;                        // reduction slices of segment 1 / 2
+  int b_early;                               // first B tile fetched before griddepcontrol.wait (rc_gemm.b_static, plain B)
 };
 
 __device__ __forceinline__ float apply_op(const rc_operand& o, float v, int row, int col) {
@@ -129,16 +130,13 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
 #pragma unroll
   for (int i = 0; i < A_IT; ++i) csum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto load_tile = [&](int t) {
+  auto load_a = [&](int t) {
     const bool seg2 = t >= p.tiles1;
     const int k0 = (seg2 ? t - p.tiles1 : t) * kRK;
     const int kk = seg2 ? g.k2 : g.k;
     const float* abase = seg2 ? g.a2 : g.a.ptr;
     const int lda = seg2 ? g.lda2 : g.a.ld;
     const bool avec = seg2 ? p.a2_vec : p.a_vec;
-    const float* bbase = seg2 ? g.b2 : g.b.ptr;
-    const int ldb = seg2 ? g.ldb2 : g.b.ld;
-    const bool bvec = seg2 ? p.b2_vec : p.b_vec;
 #pragma unroll
     for (int it = 0; it < A_IT; ++it) {
       const int s = tid + it * kGemmThreads;
@@ -151,6 +149,14 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
         else                ra[it] = load_op4(g.a, abase, lda, k0 + row, m0 + c4, kk, g.m, avec, !seg2);
       }
     }
+  };
+  auto load_b = [&](int t) {
+    const bool seg2 = t >= p.tiles1;
+    const int k0 = (seg2 ? t - p.tiles1 : t) * kRK;
+    const int kk = seg2 ? g.k2 : g.k;
+    const float* bbase = seg2 ? g.b2 : g.b.ptr;
+    const int ldb = seg2 ? g.ldb2 : g.b.ld;
+    const bool bvec = seg2 ? p.b2_vec : p.b_vec;
 #pragma unroll
     for (int it = 0; it < B_IT; ++it) {
       const int s = tid + it * kGemmThreads;
@@ -159,6 +165,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
       else                rb[it] = load_op4(g.b, bbase, ldb, k0 + row, n0 + c4, kk, g.n, bvec, !seg2);
     }
   };
+  auto load_tile = [&](int t) { load_a(t); load_b(t); };
   auto store_tile = [&](int stage) {
     float* as = As + stage * A_STAGE;
     float* bs = Bs + stage * B_STAGE;
@@ -179,9 +186,20 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
     }
   };
 
-  if (t_beg < t_end) {
-    load_tile(t_beg);
+  // Programmatic dependent launch (rc_common.cuh): this CTA may be resident while the kernel before it still runs.
+  // A parameter operand (b_static) is fetched before waiting for that kernel - a 64 KB weight tile per CTA at the
+  // reference shape, the longest memory round trip of these few-microsecond kernels.
+  if (p.b_early && t_beg < t_end) {
+    load_b(t_beg);
+    pdl_entry();
+    load_a(t_beg);
     store_tile(0);
+  } else {
+    pdl_entry();
+    if (t_beg < t_end) {
+      load_tile(t_beg);
+      store_tile(0);
+    }
   }
   __syncthreads();
   // Warp-split reduction for the latency-bound shape (8-row tile, 128-long slices - every Linear of the reference

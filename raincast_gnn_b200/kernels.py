@@ -102,11 +102,13 @@ def operand(t, ld, op=RC_OP_NONE, p=(None, None, None, None), aux=None, ld_aux=0
 def gemm(m, n, k, a: _lib.rc_operand, b: _lib.rc_operand, d, ldd, *, a_layout=RC_A_ROW, b_layout=RC_B_COL, bias=None,
          bias_scale=1.0, epi=RC_EPI_NONE, res=None, ld_res=0, bits_out=None, ld_bits_out=0, e_aux=None, ld_e_aux=0,
          e_p=(None, None, None, None), stats=None, splits=1, split_stride=0, colsum_a=None, a2=None, lda2=0, b2=None,
-         ldb2=0, k2=0, rows_per_warp=0, a_out=None, ld_a_out=0, run=True):
+         ldb2=0, k2=0, rows_per_warp=0, a_out=None, ld_a_out=0, b_static=None, run=True):
+    if b_static is None:            # activation GEMMs: B is a parameter, fetched before the wait on the previous kernel
+        b_static = a_layout == RC_A_ROW
     g = _lib.rc_gemm(m, n, k, a_layout, b_layout, a, b, _lib.ptr(a2), lda2, _lib.ptr(b2), ldb2, k2, _lib.ptr(d), ldd,
                      _lib.ptr(bias), bias_scale, epi, _lib.ptr(res), ld_res, _lib.ptr(bits_out), ld_bits_out,
                      _lib.ptr(e_aux), ld_e_aux, _lib.ptr(e_p[0]), _lib.ptr(e_p[1]), _lib.ptr(e_p[2]), _lib.ptr(e_p[3]),
-                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp, None, 0, _lib.ptr(a_out), ld_a_out)
+                     _lib.ptr(stats), splits, split_stride, _lib.ptr(colsum_a), rows_per_warp, None, 0, _lib.ptr(a_out), ld_a_out, int(b_static))
     if run:
         L = _lib.lib()
         ws_bytes = int(L.rc_gemm_tc_workspace(C.byref(g)))     # > 0: large activation GEMM -> tensor cores (3xTF32)
@@ -282,7 +284,8 @@ def dimred_prepack(P, f, x=None):
         if x is not None:
             m = x.shape[0]
             xw = _new((m, n), torch.float32, x.device)
-            gemm(m, n, f, operand(x, f), operand(pack["wx"], pack["wx"].shape[1]), xw, n, bias=P["dimred_b"])
+            gemm(m, n, f, operand(x, f), operand(pack["wx"], pack["wx"].shape[1]), xw, n, bias=P["dimred_b"],
+                 b_static=False)     # wx was written by the copy kernel just before this one on the side stream
             pack["xw"] = xw
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
