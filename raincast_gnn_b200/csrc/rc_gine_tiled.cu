@@ -139,10 +139,14 @@ __device__ __forceinline__ void produce_tiles(const float* __restrict__ src, siz
       // gathered rows: the row addresses are broadcast lane by lane; every lane moves 16 bytes of every row of the warp
       const int cnt = nst > warp ? (nst - warp + kProdWarps - 1) / kProdWarps : 0;
       unsigned char* dst0 = rows + (size_t)warp * kTileRowBytes + 16 * lane;
+#ifndef RC_TILED_NO_GATHER      // (tools/build_variant.sh nogather -DRC_TILED_NO_GATHER: everything but the row gather, to time the SM-side floor)
       for (int k = 0; k < cnt; ++k) {
         const unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)my_src, k) + 16 * lane;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst0 + k * (kProdWarps * kTileRowBytes))), "l"(sp) : "memory");
       }
+#else
+      (void)cnt; (void)dst0; (void)my_src;
+#endif
     }
     const bool last = tile >= t.n_tiles;      // (dynamic schedule only: tells the consumers to stop)
     if (warp == 0 && lane == 0) {

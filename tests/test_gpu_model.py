@@ -164,6 +164,22 @@ def test_train_step_matches_reference_fixture(dev, golden_model, name):
     model.eval()
     with torch.no_grad():
         assert rel_err(model(b).cpu().numpy(), golden_model[f"{name}.eval.preds"]) < TOL
+    # and the gate without any allowance: a fresh model, the ReLU decisions of its CUDA backward forced into the float64
+    # restatement (oracle/masked.py) - every gradient tensor within 1e-5
+    from oracle import masked
+    from test_gpu_masked_parity import check_masks_are_float64_decisions, cuda_step_with_masks
+    _, batch2, model2, sd2 = build_case(name, dev)
+    _, l2, grads, masks = cuda_step_with_masks(model2.train(), batch2, dev)
+    kw = _model_kw(c)
+    args = dict(num_layers=c["layers"], loss=c["loss"], grad_u=c["grad_u"], u=kw["u"], xi=kw["xi"])
+    cpu_masks = {k: v.cpu() for k, v in masks.items()}
+    _, _, _, own = masked.loss_and_grads(sd2, batch2, **args)
+    check_masks_are_float64_decisions(cpu_masks, own)
+    _, lm, gm, _ = masked.loss_and_grads(sd2, batch2, masks=cpu_masks, **args)
+    assert abs(l2.item() - lm.item()) < TOL * abs(lm.item())
+    for k, gr in grads.items():
+        scale = grad_scale(k, gm[k].abs().max().item(), lambda kk: gm[kk].abs().max().item())
+        assert (gr.cpu().double() - gm[k]).abs().max().item() / scale < TOL, k
 
 
 @pytest.mark.parametrize("name", ["tiny_mixed_u", "ref_mixed_u"])
