@@ -103,7 +103,7 @@ extern "C" int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred,
   CrpsWs ws = crps_ws(workspace);
   const int m = num_nodes;
   const int ncnt = crps_count_blocks(m);
-  const int blocks = ceil_div(m < 1 ? 1 : m, kCrpsThreads);
+  const int blocks = crps_main_blocks(m);
   const CrpsCountP pc{y, m, ws.cnt};
   const CrpsMainP pm{pred, y, d_pred, m, kind, raw_input, u_fixed, xi, t, ws.cnt, ncnt, ws.loss};
   const CrpsFinalP pf{ws.cnt, ncnt, ws.loss, blocks, loss_out, n_valid};

@@ -54,6 +54,11 @@ struct PostBwdP {
 
 constexpr int kCrpsThreads = 256;
 constexpr int kCountBlocksMax = 256;
+constexpr int kCrpsMainBlocksMax = 148 * 8;      // CTAs of the main kernel (grid-stride over 256-node tiles)
+__host__ __device__ inline int crps_main_blocks(int m) {
+  const int b = ceil_div(m < 1 ? 1 : m, kCrpsThreads);
+  return b > kCrpsMainBlocksMax ? kCrpsMainBlocksMax : b;
+}
 
 __host__ __device__ inline int crps_count_blocks(int m) {
   int b = ceil_div(m, kCrpsThreads * 4);
@@ -78,8 +83,20 @@ __device__ __forceinline__ void crps_count_tile(const CrpsCountP& p, const uint3
   int* cnt_partial = p.cnt_partial;
   (void)bid; (void)gdim;
 
+  // 16 targets per thread and pass (four independent 128-bit loads): with <= 256 CTAs a scalar grid-stride loop had one
+  // 128-byte request in flight per warp and took 250 us for 2^24 targets - longer than the CRPS kernel itself
   int local = 0;
-  for (int i = bid.x * 256 + threadIdx.x; i < m; i += gdim.x * 256) local += !isnan(y[i]);
+  const bool vec = (reinterpret_cast<uintptr_t>(y) & 15u) == 0;
+  const int m16 = vec ? (m / 16) * 16 : 0;
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  for (int i = (bid.x * 256 + threadIdx.x) * 4; i < m16 / 4; i += gdim.x * 256 * 4) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(y4 + i + k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) local += !isnan(v[k].x) + !isnan(v[k].y) + !isnan(v[k].z) + !isnan(v[k].w);
+  }
+  for (int i = m16 + bid.x * 256 + threadIdx.x; i < m; i += gdim.x * 256) local += !isnan(y[i]);
   __shared__ int sh[kCrpsThreads / 32];
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
@@ -117,21 +134,73 @@ __device__ __forceinline__ void crps_main_tile(const CrpsMainP& p, const uint3 b
   }
   __syncthreads();
   const float inv_n = s_cnt > 0 ? 1.0f / (float)s_cnt : 0.0f;
-  const int i = bid.x * 256 + threadIdx.x;
+  // The block's 256 rows of WIDTH floats are one contiguous span: it is moved with 128-bit coalesced accesses through
+  // shared memory (a row-strided access pattern made every store instruction touch all 20 sectors of a warp's span
+  // with 4-byte pieces).  A thread reads and writes only its own WIDTH slots of the tile (stride WIDTH: odd or 2, 4).
+  __shared__ __align__(16) float tile_in[kCrpsThreads * WIDTH];
+  __shared__ __align__(16) float tile_out[kCrpsThreads * WIDTH];
+  const int tid = threadIdx.x;
+  const bool in_vec = (reinterpret_cast<uintptr_t>(pred) & 15u) == 0, out_vec = (reinterpret_cast<uintptr_t>(d_pred) & 15u) == 0;
+  constexpr int kF4 = kCrpsThreads * WIDTH / 4;                   // 128-bit pieces of a full tile
+  constexpr int kPer = (kF4 + kCrpsThreads - 1) / kCrpsThreads;   // per thread: 1 (WIDTH <= 4) or 2
   float loss = 0.0f;
-  if (i < m) {
-    const float yi = y[i];
-    float row[WIDTH], g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  // a CTA walks tiles bid.x, bid.x + gridDim.x, ... (<= kCrpsMainBlocksMax CTAs: the valid-count prologue and the
+  // loss partial are paid once per CTA, and the final reduction reads a few hundred partials instead of M / 256).
+  // The next tile's rows and targets are fetched into registers before the current tile is computed.
+  float4 nx[kPer];
+  float ny = 0.f;
+  auto fetch = [&](int base) {
+    if (base >= m) return;
+    const bool full = m - base >= kCrpsThreads;
+    if (full && in_vec) {
+      const float4* s4 = reinterpret_cast<const float4*>(pred + (size_t)base * WIDTH);
 #pragma unroll
-    for (int j = 0; j < WIDTH; ++j) row[j] = pred[(size_t)i * WIDTH + j];
-    if (!isnan(yi)) loss = crps_node_k<WIDTH - 2>(row, yi, raw_input, u_fixed, xi, t, g);
+      for (int q = 0; q < kPer; ++q)
+        if (tid + q * kCrpsThreads < kF4) nx[q] = __ldcs(s4 + tid + q * kCrpsThreads);
+    }
+    ny = base + tid < m ? __ldcs(y + base + tid) : nanf("");
+  };
+  const int stride = gdim.x * kCrpsThreads;
+  fetch(bid.x * kCrpsThreads);
+  for (int base = bid.x * kCrpsThreads; base < m; base += stride) {
+    const int n_here = min(kCrpsThreads, m - base);
+    const bool full = n_here == kCrpsThreads;
+    if (full && in_vec) {
+#pragma unroll
+      for (int q = 0; q < kPer; ++q)
+        if (tid + q * kCrpsThreads < kF4) reinterpret_cast<float4*>(tile_in)[tid + q * kCrpsThreads] = nx[q];
+    } else {
+      const float* src = pred + (size_t)base * WIDTH;
+      for (int k = tid; k < n_here * WIDTH; k += kCrpsThreads) tile_in[k] = src[k];
+    }
+    const int i = base + tid;
+    const float yi = ny;
+    __syncthreads();                 // tile_in complete (and every thread is past the stores out of tile_out of the pass before)
+    fetch(base + stride);
+    {
+      float row[WIDTH], g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < WIDTH; ++j) row[j] = tile_in[tid * WIDTH + j];
+      if (i < m && !isnan(yi)) loss += crps_node_k<WIDTH - 2>(row, yi, raw_input, u_fixed, xi, t, g);
+#pragma unroll
+      for (int j = 0; j < WIDTH; ++j) tile_out[tid * WIDTH + j] = g[j] * inv_n;
+    }
+    __syncthreads();                 // tile_out complete; tile_in may be overwritten
     if (d_pred != nullptr) {
+      float* dst = d_pred + (size_t)base * WIDTH;
+      if (full && out_vec) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-      for (int j = 0; j < WIDTH; ++j) d_pred[(size_t)i * WIDTH + j] = g[j] * inv_n;
+        for (int q = 0; q < kPer; ++q)
+          if (tid + q * kCrpsThreads < kF4) __stcs(d4 + tid + q * kCrpsThreads, reinterpret_cast<const float4*>(tile_out)[tid + q * kCrpsThreads]);
+      } else {
+        for (int k = tid; k < n_here * WIDTH; k += kCrpsThreads) dst[k] = tile_out[k];
+      }
     }
   }
-  double dl = warp_sum((double)loss);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dl;
+  // 32 node losses in fp32 (fixed shuffle order), warps and blocks in float64
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = (double)loss;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
