@@ -18,6 +18,14 @@ fp32): forward, CRPS, backward, gradient all-reduce (N > 1), AdamW.  Prints ONE 
            backward kernel and for the graph shape where HBM, not the SM, is the relevant bound
            `deepsets_contraction`: the tcgen05 member contraction at the config-4 / config-5 shapes (TFLOP/s issued
            against the measured dense peak, ensemble read rate against the HBM peak)
+           `crps`: the links + mixture-CRPS kernel at 2^24 nodes against (2C+1)*4 bytes per node
+  step_roofline — FLOPs and bytes of one reference-shape step against the measured fp32 FMA peak (rc_debug_fma_peak)
+           and the HBM peak: how far the launch-bound step is from either floor
+  gpu_eager_baseline — the oracle's modules (plain PyTorch ops, library kernels) run eagerly on the same GPU
+  config4 / config5 — whole training step (ms) of one 100k-node graph, 51 members: H=128 fp32 / H=512 bf16 DeepSets
+  train_loop_e2e — raincast_gnn_b200.train.run_epoch_engine over a shuffled DataLoader (host collate included), wall clock
+  dp_check — data-parallel semantics: the engine's emulated-rank step against the micro-batch oracle (N = 1), replicas
+           bit-identical and losses equal to the NCCL exchange (N > 1)
   cpu_baseline — the CPU oracle (reference modules' arithmetic, oracle/) timed on this box's host cores
 """
 from __future__ import annotations
@@ -278,6 +286,30 @@ def measure_deepsets_contraction(dev, peaks, iters: int = 5):
                     "ens_read_gbs": ens.numel() * 4 / ms / 1e6, "frac_hbm": ens.numel() * 4 / ms / 1e6 / peaks["hbm_gbs"]}
         del w1, b1, pooled
     return out
+
+
+def measure_crps(dev, peaks, log2_m: int = 24, iters: int = 5):
+    """The links + mixture-CRPS kernel (value + gradient, MixedLoss with learned u, raw head input) at M = 2^24 nodes:
+    whole rc_crps_fwd_bwd call (count + main + final kernels) against (2C+1)*4 algorithmic bytes per node."""
+    from raincast_gnn_b200 import kernels as K
+    from raincast_gnn_b200.utils import synthetic as syn
+    mm, width = 1 << log2_m, 5
+    raw = torch.randn(mm, width, device=dev)
+    y = syn.log_precip_targets(mm, seed=5).to(dev)
+    for _ in range(3):
+        K.crps_fwd_bwd(raw, y, 3, raw_input=True)
+    torch.cuda.synchronize()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        K.crps_fwd_bwd(raw, y, 3, raw_input=True)
+    c.record()
+    c.synchronize()
+    ms = a.elapsed_time(c) / iters
+    by = (2 * width + 1) * 4 * mm
+    return {"workload": f"MixedLoss(grad_u) value + gradient, raw head input, M = 2^{log2_m} nodes (inputs 11x L2: no flush needed)",
+            "us_per_launch": ms * 1e3, "algorithmic_bytes": by, "achieved": by / ms / 1e6, "unit": "GB/s",
+            "frac": by / ms / 1e6 / peaks["hbm_gbs"]}
 
 
 def measure_fp32_peak(dev):
@@ -565,6 +597,10 @@ def run_b200(args):
                 line["roofline"]["deepsets_contraction"] = measure_deepsets_contraction(dev, peaks)
             except Exception as exc:        # never lose the bench line over the extra leg
                 line["roofline"]["deepsets_contraction"] = {"error": repr(exc)}
+            try:        # third north-star kernel: links + mixture CRPS
+                line["roofline"]["crps"] = measure_crps(dev, peaks)
+            except Exception as exc:
+                line["roofline"]["crps"] = {"error": repr(exc)}
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     tr = json.load(f)
