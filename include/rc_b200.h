@@ -341,15 +341,20 @@ int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, f
                       int64_t* step, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                       void* stream);
 /* The same exchange as ONE kernel after backward: rc_p2p_step waits (inside the kernel) until every rank has published
- * its gradients of exchange *epoch + 1, sums them in rank order, applies AdamW, advances *step and *epoch and publishes
- * "done reading"; rc_p2p_wait_done - launched at the start of the NEXT step, off the critical path - waits until every
- * peer is done reading this rank's gradients before they are overwritten.  flags: as rc_p2p_barrier (slot 0 = published,
- * slot 1 = done reading); epoch: this rank's int32[1], zero before first use, never reset (it must advance in lock step
- * on all ranks: every rank calls rc_p2p_step the same number of times). */
+ * its gradients of exchange *epoch + 1, sums them in rank order, applies AdamW, advances *step and *epoch, publishes
+ * "done reading" as soon as this rank holds the peers' gradients in registers, and ends only when every peer has done
+ * the same - so the caller may overwrite its gradients as soon as the kernel has completed (no second call).
+ * flags: as rc_p2p_barrier (slot 0 = published, slot 1 = done reading); epoch: this rank's int32[1], zero before first
+ * use, never reset (it must advance in lock step on all ranks: every rank calls rc_p2p_step the same number of times).
+ * rc_p2p_wait_done is the stand-alone wait for slot 1 (callers that build the exchange from the barriers).
+ * rc_p2p_flag_scope(1): device-scope fences + relaxed system-scope flag accesses instead of the library default
+ * st.release.sys / fence.acq_rel.sys (7-8 us per step cheaper on an NVSwitch box; rc_p2p.cu states why it is sufficient
+ * for flags that guard data written by earlier kernels). */
 int rc_p2p_step(float* param, const float* const* peer_grads, int32_t* const* flags, int32_t* epoch, int rank, int world,
                 float* exp_avg, float* exp_avg_sq, int64_t* step, long long n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, int32_t* timed_out, void* stream);
 int rc_p2p_wait_done(int32_t* const* flags, const int32_t* epoch, int rank, int world, int32_t* timed_out, void* stream);
+int rc_p2p_flag_scope(int device_scope_fences);
 
 /* ------------------------------------------------------------------------------------------------
  * Test instrumentation: the ReLU decisions of the backward kernels as bit masks (bit c % 32 of word c / 32 per row).
@@ -367,7 +372,8 @@ int rc_debug_bn_relu_mask(const float* t, int ld, const float* mean, const float
 int rc_debug_fma_peak(float* scratch, int iters, double* flops, void* stream);
 /* tensor-core GEMM timeline of CTA 0 (tools/trace_gemm_tc.py) */
 void rc_debug_tc_trace(void* device_buf);
-/* rc_p2p_step: globaltimer (ns) of CTA 0 at entry, flags published, all ranks arrived, update done, exit: int64[5] */
+/* rc_p2p_step: globaltimer (ns) of CTA 0 at entry, flags published, all ranks arrived, update done, exit; rc_p2p_wait_done:
+ * entry, exit: int64[8] (set before a CUDA graph capture to trace replays) */
 void rc_debug_p2p_trace(void* device_buf);
 /* tensor-core DeepSets pool backward: clocks of CTA 0, int64 [8 events][32 stages] (tools/trace_pool_bwd.py) */
 void rc_debug_ds_trace(void* device_buf);

@@ -103,6 +103,7 @@ def _declare(lib):
         "rc_p2p_adamw_step": (i, [p, p, i, p, p, p, ll, f, f, f, f, f, p]),
         "rc_p2p_step": (i, [p, p, p, p, i, i, p, p, p, ll, f, f, f, f, f, p, p]),
         "rc_p2p_wait_done": (i, [p, p, i, i, p, p]),
+        "rc_p2p_flag_scope": (i, [i]),
         "rc_debug_gine_msg_mask": (i, [p, p, p, p, p, i, i, i, p, p]),
         "rc_debug_bn_relu_mask": (i, [p, i, p, p, p, p, i, i, p, p]),
         "rc_debug_fma_peak": (i, [p, i, p, p]),

@@ -74,7 +74,8 @@ class TrainEngine:
         # memory), and the step sums the peers' gradients inside the AdamW kernel instead of an NCCL all-reduce
         self.p2p = None
         self.flat_g = None
-        if self.world > 1 and os.environ.get("RC_DP_EXCHANGE", "p2p") == "p2p":
+        force = os.environ.get("RC_DP_FORCE_P2P", "0") == "1" and process_group is not None     # (measurements: the exchange path at world 1)
+        if (self.world > 1 or force) and os.environ.get("RC_DP_EXCHANGE", "p2p") == "p2p":
             self.flat_g = self._setup_peer_exchange(total, dev)
         if self.flat_g is None:
             self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -121,6 +122,9 @@ class TrainEngine:
             h_flat = symm.rendezvous(flat, group)
             h_flags = symm.rendezvous(flags, group)
             torch.cuda.synchronize(dev)
+            # flag protocol of the exchange kernel: device-scope fences by default (rc_p2p.cu), RC_P2P_STRICT=1 keeps
+            # release / acquire at system scope
+            _lib.check(_lib.lib().rc_p2p_flag_scope(0 if os.environ.get("RC_P2P_STRICT", "0") == "1" else 1), "rc_p2p_flag_scope")
             torch.distributed.barrier(group)          # every rank's flags are zero before anyone signals
             self.p2p = {"rank": rank, "grads": h_flat.buffer_ptrs_dev, "flags": h_flags.buffer_ptrs_dev,
                         "epochs": torch.zeros(2, dtype=torch.int32, device=dev),
@@ -182,16 +186,6 @@ class TrainEngine:
     def _fwd_bwd_body(self):
         blk = self._blocks
         Pd, Gd = blk["ds"]
-        done_reading = None
-        if self.p2p is not None:
-            # the peers have finished reading this rank's gradients of the previous step (they may now be overwritten):
-            # waited for on the side stream while the forward runs; the backward below waits for the event
-            P = self.p2p
-            with K.on_side():
-                _lib.check(_lib.lib().rc_p2p_wait_done(P["flags"], P["epochs"].data_ptr(), P["rank"], self.world, P["timed_out"].data_ptr(),
-                                                       torch.cuda.current_stream(self.device).cuda_stream), "rc_p2p_wait_done")
-                done_reading = torch.cuda.Event()
-                done_reading.record(torch.cuda.current_stream(self.device))
         K.dimred_prepack(blk["dr"][0], self.feats, self.x)   # side stream, overlaps the DeepSets kernels
         emb, s_ds = K.deepsets_fwd(Pd, self.ens, bf16=(getattr(self.model.deepset, "compute_dtype", "fp32") == "bf16"))
         Pr, Gr = blk["dr"]
@@ -205,8 +199,6 @@ class TrainEngine:
         raw, s_h = K.head_fwd(Ph, h)
         _, d_raw, _ = K.crps_fwd_bwd(raw, self.y, self.kind, raw_input=True, u=self.u_fixed, xi=self.xi, t=self.t,
                                      loss_out=self.loss)
-        if done_reading is not None:
-            torch.cuda.current_stream(self.device).wait_event(done_reading)
         d = K.head_bwd(Ph, s_h, d_raw, Gh)
         for i in reversed(range(len(blk["layers"]))):
             Pl, Gl = blk["layers"][i]
@@ -215,8 +207,11 @@ class TrainEngine:
         K.deepsets_bwd(Pd, s_ds, d_emb, Gd)
 
     def _optimizer(self):
+        if self.p2p is not None and os.environ.get("RC_DP_DEBUG_LOCAL_ADAMW", "0") == "1":
+            return self._adamw_call()         # (measurement only: peer-mapped gradient buffer, no exchange)
         if self.p2p is not None:
-            # ONE kernel: wait for every rank's gradients, sum them from peer memory in rank order, AdamW, publish "done reading"
+            # ONE kernel: wait for every rank's gradients, sum them from peer memory in rank order, AdamW; it ends once every
+            # peer is done reading this rank's gradients, so the next step needs no handshake before its backward
             L, P, st = _lib.lib(), self.p2p, torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(L.rc_p2p_step(self.flat_p.data_ptr(), P["grads"], P["flags"], P["epochs"].data_ptr(), P["rank"], self.world,
                                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), self.n_params,

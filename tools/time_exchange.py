@@ -34,7 +34,7 @@ def timed():
 
 eng._optimizer = timed
 from raincast_gnn_b200 import _lib
-trace = torch.zeros(5, dtype=torch.int64, device=dev)
+trace = torch.zeros(8, dtype=torch.int64, device=dev)
 for it in range(30):
     if it == 25:
         _lib.lib().rc_debug_p2p_trace(trace.data_ptr())
