@@ -308,7 +308,7 @@ extern "C" int rc_p2p_step(float* param, const float* const* peer_grads, int32_t
   if (n % 4 || !aligned16(param) || !aligned16(exp_avg) || !aligned16(exp_avg_sq))
     return fail(RC_ERR_ARG, "rc_p2p_step: n must be a multiple of 4 and the buffers 16-byte aligned");
   long long blocks = ceil_div_ll(n / 4, 256);
-  if (blocks > kNumSMs) blocks = kNumSMs;          // every CTA polls the peers' flags: all of them must be resident
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;  // (a CTA waits for flags that PEERS set, never for another local CTA: no residency requirement)
   if (blocks < 1) blocks = 1;
   P2pAdamP p;
   p.grads = peer_grads;
