@@ -233,6 +233,42 @@ def test_gine_aggregation_fwd_bwd(dev, golden_graph, name, batch, h):
     assert rel_err(_np(de), eps.grad.numpy()) < TOL
 
 
+@pytest.mark.parametrize("name,batch,h,hid", [("ref122_d100", 8, 128, 128), ("asym23", 3, 32, 64), ("n40_d150", 4, 256, 128)])
+def test_gine_aggregation_as_gemm_prologue_is_bit_identical(dev, golden_graph, name, batch, h, hid):
+    """N1: the aggregation fused into the layer's first Linear (RC_OP_GINE_AGGR A-operand prologue + a_out) against the
+    stand-alone aggregation kernel followed by the same GEMM: identical bits in the aggregate, the Linear output and the
+    BatchNorm tile statistics."""
+    from oracle import graph as og
+    from raincast_gnn_b200 import graph as G, kernels as K
+    ei, ea = golden_graph[f"{name}.edge_index"], golden_graph[f"{name}.edge_attr"]
+    n = int(ei.max()) + 1
+    ei_b, ea_b = og.collate_edges(ei, ea, n, batch)
+    m = n * batch
+    sg = G.build_station_graph(torch.from_numpy(ei_b), torch.from_numpy(ea_b), m).to(dev)
+    g = torch.Generator().manual_seed(h + m)
+    x = torch.randn(m, h, generator=g).to(dev)
+    w_e, b_e = torch.randn(h, generator=g).to(dev), torch.randn(h, generator=g).to(dev)
+    eps = torch.tensor([0.3], device=dev)
+    w0 = (torch.randn(hid, h, generator=g) / h ** 0.5).to(dev)
+    b0 = torch.randn(hid, generator=g).to(dev)
+    # two kernels
+    agg = torch.empty(m, h, device=dev)
+    K.gine_aggr_fwd(x, sg, w_e, b_e, eps, agg, tiled=False)
+    row_tile = K.gemm_row_tile(m, hid, h)
+    tiles = -(-m // row_tile)
+    t_two, st_two = torch.empty(m, hid, device=dev), torch.empty(tiles, 2, hid, device=dev)
+    K.gemm(m, hid, h, K.operand(agg, h), K.operand(w0, h), t_two, hid, bias=b0, epi=K.RC_EPI_BN_STATS, stats=st_two)
+    # one kernel
+    agg_one = torch.full((m, h), float("nan"), device=dev)
+    t_one, st_one = torch.empty(m, hid, device=dev), torch.empty(tiles, 2, hid, device=dev)
+    a_op = K.operand(x, h, K.RC_OP_GINE_AGGR, (w_e, b_e, eps, None), aux=sg.attr, idx0=sg.rowptr, idx1=sg.col)
+    K.gemm(m, hid, h, a_op, K.operand(w0, h), t_one, hid, bias=b0, epi=K.RC_EPI_BN_STATS, stats=st_one, a_out=agg_one, ld_a_out=h)
+    torch.cuda.synchronize()
+    assert torch.equal(agg_one, agg)
+    assert torch.equal(t_one, t_two)
+    assert torch.equal(st_one, st_two)
+
+
 # ------------------------------------------------------------------------------------------------ DeepSets
 @pytest.mark.parametrize("m,em,f,h", [(976, 11, 35, 128), (30, 4, 7, 32), (100, 51, 35, 128), (64, 10, 35, 256), (17, 3, 5, 32),
                                        (50, 6, 64, 128), (333, 7, 20, 200)])

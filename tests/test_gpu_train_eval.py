@@ -99,3 +99,50 @@ def test_train_cli_resident(run_dir):
     assert os.path.isfile(ckpt)
     log = open(os.path.join(run_dir, "logs", "train_1.log")).read()
     assert "resident on" in log and "[Train] Loss:" in log
+
+
+def test_epoch_with_ragged_last_batch_matches_reference_loop(run_dir):
+    """train.py:55-74 trains on every batch of the DataLoader, the ragged last one included (12 dates, batch 8 -> 8 + 4).
+    The engine steps the full batch through its captured graph and the ragged one eagerly; the epoch must leave the same
+    parameters and the same mean loss as the reference loop (module API + torch.optim.AdamW) on the same batches."""
+    import copy
+    from raincast_gnn_b200 import train as rc_train
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.pyg_compat import DataLoader
+    from raincast_gnn_b200.utils.dataset import SyntheticEUPPBench
+    cfg = json.load(open(os.path.join(run_dir, "params.json")))
+    dev = torch.device("cuda:0")
+    ds = SyntheticEUPPBench(n_dates=12, seed=3)
+    loader = DataLoader(ds, batch_size=8, shuffle=False)
+    sizes = [b.x.shape[0] for b in loader]
+    assert sizes == [8 * 122, 4 * 122]
+    torch.manual_seed(1)
+    model_a = GNN(35, cfg["gnn_hidden"], cfg["gnn_hidden"], cfg["gnn_layers"], torch.optim.AdamW, {"lr": 1e-3}, cfg["loss"],
+                  cfg["grad_u"], cfg["u"], cfg["xi"]).to(dev).train()
+    model_b = copy.deepcopy(model_a)
+    # reference loop
+    opt = torch.optim.AdamW(model_a.parameters(), lr=1e-3)
+    ref_losses = []
+    for b in loader:
+        b = b.to(dev)
+        loss = model_a.loss_fn.crps(model_a(b), b.y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss))
+    # engine epoch
+    first = next(iter(loader))
+    eng = TrainEngine(model_b, first.station_graph, first.x.shape[0], 11, 35, lr=1e-3).capture()
+    mean_loss = rc_train.run_epoch_engine(eng, loader)
+    assert int(eng.step_count) == 2
+    assert abs(mean_loss - sum(ref_losses) / 2) < 1e-5 * abs(sum(ref_losses) / 2)
+    for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        # Adam's first steps move every element by ~lr * m / sqrt(v): a skipped or doubled step would shift almost
+        # every element by ~1e-3 = lr.  The normalisation amplifies the RELATIVE error of an element's gradient, and fp32
+        # kernels are only max-norm accurate, so single elements with a small gradient may differ by a few percent of
+        # lr (all of them where the true gradient is 0: the bias in front of BatchNorm); the mean over a tensor may not.
+        d = (pa - pb).abs().flatten()
+        assert d.max().item() < 0.5e-3, k
+        if not k.endswith(".nn.0.bias"):
+            assert d.mean().item() < 0.02 * 1e-3, k
