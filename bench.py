@@ -520,7 +520,7 @@ def run_b200(args):
             if world > 1:
                 # the un-timed L2 flush lets the ranks drift apart; without re-aligning them here (device side, no host
                 # sync) the drift would be measured as part of the next step's gradient exchange
-                torch.distributed.all_reduce(align, group=pg)
+                eng.align_ranks()
             a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if e2e:
@@ -561,7 +561,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "parallelism": (f"dp{world} (dates sharded; per step one exchange of {eng.n_params} fp32 gradients: " +
                                        ("waited for, summed from NVLink peer memory and applied by ONE kernel inside the captured step)" if eng.p2p is not None else "one NCCL all-reduce)"))
                                       if world > 1 else "single GPU (dates would be sharded rank::world; no gradient exchange)",
-                       "timing": "per-step CUDA events on the launch stream; 256 MiB L2 flush between timed steps, outside the events (N > 1: the ranks are re-aligned by a device-side collective after the flush, also outside the events); max over ranks",
+                       "timing": "per-step CUDA events on the launch stream; 256 MiB L2 flush between timed steps, outside the events (N > 1: the ranks are re-aligned by a device-side barrier over peer-memory flags after the flush, also outside the events); max over ranks",
                        "cuda_graph": True, "final_loss": final_loss},
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / K_steps},

@@ -117,10 +117,13 @@ class TrainEngine:
             rank = torch.distributed.get_rank(group)
             flat = symm.empty(total, dtype=torch.float32, device=dev)
             flags = symm.empty(2 * 16, dtype=torch.int32, device=dev)
+            flags2 = symm.empty(2 * 16, dtype=torch.int32, device=dev)      # align_ranks(): a barrier of its own
             flat.zero_()
             flags.zero_()
+            flags2.zero_()
             h_flat = symm.rendezvous(flat, group)
             h_flags = symm.rendezvous(flags, group)
+            h_flags2 = symm.rendezvous(flags2, group)
             torch.cuda.synchronize(dev)
             # flag protocol of the exchange kernel: device-scope fences by default (rc_p2p.cu), RC_P2P_STRICT=1 keeps
             # release / acquire at system scope
@@ -128,7 +131,8 @@ class TrainEngine:
             torch.distributed.barrier(group)          # every rank's flags are zero before anyone signals
             self.p2p = {"rank": rank, "grads": h_flat.buffer_ptrs_dev, "flags": h_flags.buffer_ptrs_dev,
                         "epochs": torch.zeros(2, dtype=torch.int32, device=dev),
-                        "timed_out": torch.zeros(1, dtype=torch.int32, device=dev), "keep": (flat, flags, h_flat, h_flags)}
+                        "timed_out": torch.zeros(1, dtype=torch.int32, device=dev), "keep": (flat, flags, h_flat, h_flags, flags2, h_flags2),
+                        "align_flags": h_flags2.buffer_ptrs_dev, "align_epochs": torch.zeros(2, dtype=torch.int32, device=dev)}
             return flat
         except Exception as exc:                      # no symmetric memory on this box / torch build: NCCL path
             import logging
@@ -284,6 +288,20 @@ class TrainEngine:
                                               dates.data_ptr(), b, len(split), n * self.feats, n * self.members * self.feats, n,
                                               self.x.data_ptr(), self.ens.data_ptr(), self.y.data_ptr(), self._bad_date.data_ptr(),
                                               torch.cuda.current_stream(self.device).cuda_stream), "rc_gather_dates")
+
+    def align_ranks(self):
+        """A device-side barrier of the ranks on the current stream (peer-memory flags of its own, one tiny kernel, no host
+        synchronisation): every rank leaves it within a flag round trip of the last one's arrival.  bench.py calls it
+        between its un-timed L2 flush and a timed step; without peer memory it falls back to a one-element all-reduce."""
+        if self.p2p is not None:
+            P = self.p2p
+            _lib.check(_lib.lib().rc_p2p_barrier(P["align_flags"], P["align_epochs"].data_ptr(), P["rank"], self.world, 0,
+                                                 P["timed_out"].data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+                       "rc_p2p_barrier")
+        elif self.world > 1:
+            if getattr(self, "_align", None) is None:
+                self._align = torch.zeros(1, device=self.device)
+            torch.distributed.all_reduce(self._align, group=self.pg)
 
     def check_peers(self):
         """Raise if a peer-memory barrier gave up waiting for another rank (synchronises the device)."""
