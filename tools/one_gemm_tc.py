@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from raincast_gnn_b200 import kernels as K  # noqa: E402
 
 dev = torch.device("cuda:0")
-m, h = 100000, 128
+m, h = 100000, (int(sys.argv[2]) if len(sys.argv) > 2 else 128)
 what = sys.argv[1] if len(sys.argv) > 1 else "fwd"
 g = torch.Generator(device=dev).manual_seed(0)
 x = torch.randn(m, h, generator=g, device=dev)
