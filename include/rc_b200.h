@@ -220,8 +220,8 @@ typedef struct rc_gemm {
   float* a_out; int ld_a_out;   /* the A operand after its prologue, written once (nullable): RC_OP_GINE_AGGR on the SIMT
                                    path, every prologue on the tensor-core activation path (the layer's weight-gradient
                                    GEMM then takes it as a plain operand) */
-  int b_static;                 /* 1: the B operand is a parameter - the kernel launched just before this one on the stream
-                                   does not write it.  The kernel then fetches its first B tile BEFORE waiting for that
+  int b_static;                 /* 1: the B operand is a parameter and res / e_aux are saved activations - the kernel
+                                   launched just before this one on the stream writes none of them.  The kernel then fetches its first B tile BEFORE waiting for that
                                    kernel (programmatic dependent launch), overlapping the fetch with its tail */
 } rc_gemm;
 
@@ -346,6 +346,8 @@ int rc_p2p_adamw_step(float* param, const float* const* peer_grads, int world, f
  * the same - so the caller may overwrite its gradients as soon as the kernel has completed (no second call).
  * flags: as rc_p2p_barrier (slot 0 = published, slot 1 = done reading); epoch: this rank's int32[1], zero before first
  * use, never reset (it must advance in lock step on all ranks: every rank calls rc_p2p_step the same number of times).
+ * The kernel fetches this rank's param / exp_avg / exp_avg_sq BEFORE it waits for the kernel launched before it on the
+ * stream (programmatic dependent launch): that kernel must not write them (in a training step it writes gradients).
  * rc_p2p_wait_done is the stand-alone wait for slot 1 (callers that build the exchange from the barriers).
  * rc_p2p_flag_scope(1): device-scope fences + relaxed system-scope flag accesses instead of the library default
  * st.release.sys / fence.acq_rel.sys (7-8 us per step cheaper on an NVSwitch box; rc_p2p.cu states why it is sufficient

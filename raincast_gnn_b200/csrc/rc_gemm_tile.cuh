@@ -189,6 +189,22 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
   // Programmatic dependent launch (rc_common.cuh): this CTA may be resident while the kernel before it still runs.
   // A parameter operand (b_static) is fetched before waiting for that kernel - a 64 KB weight tile per CTA at the
   // reference shape, the longest memory round trip of these few-microsecond kernels.
+  // (same promise, same place: the residual / auxiliary operand of the epilogue - a saved forward activation or the
+  // layer input - is fetched up front instead of behind the reduction, where its L2 round trip cannot overlap anything)
+  float e_pre[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool e_early = RM == 1 && p.b_early &&
+                       (g.epi == RC_EPI_RELU_RES || g.epi == RC_EPI_ADD_RES || g.epi == RC_EPI_MASK_POS || g.epi == RC_EPI_BN_RELU_BWD);
+  if (e_early) {
+    const int row = m0 + warp;
+    const bool use_res = g.epi == RC_EPI_RELU_RES || g.epi == RC_EPI_ADD_RES;
+    const float* src = use_res ? g.res : g.e_aux;
+    const int ld = use_res ? g.ld_res : g.ld_e_aux;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + ((BL == RC_B_COL) ? (lane + 32 * j) : (4 * lane + j));
+      if (row < g.m && col < g.n) e_pre[j] = __ldg(src + (size_t)row * ld + col);
+    }
+  }
   if (p.b_early && t_beg < t_end) {
     load_b(t_beg);
     pdl_entry();
@@ -370,7 +386,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
           const int row = m0 + warp * RM + i;
           float hat = 0.f, dz = 0.f;
           if (cok && row < g.m) {
-            hat = (__ldg(g.e_aux + (size_t)row * g.ld_e_aux + col) - mean) * rstd;
+            hat = ((e_early ? e_pre[j] : __ldg(g.e_aux + (size_t)row * g.ld_e_aux + col)) - mean) * rstd;
             dz = (fmaf(gamma, hat, beta) > 0.f) ? acc[i][j] : 0.f;
           }
           acc[i][j] = dz;
@@ -444,11 +460,11 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
       if (g.epi == RC_EPI_RELU) {
         v = fmaxf(v, 0.f);
       } else if (g.epi == RC_EPI_RELU_RES) {
-        v = (ok ? __ldg(g.res + (size_t)row * g.ld_res + col) : 0.f) + fmaxf(v, 0.f);
+        v = (ok ? (e_early ? e_pre[j] : __ldg(g.res + (size_t)row * g.ld_res + col)) : 0.f) + fmaxf(v, 0.f);
       } else if (g.epi == RC_EPI_ADD_RES) {
-        v += ok ? __ldg(g.res + (size_t)row * g.ld_res + col) : 0.f;
+        v += ok ? (e_early ? e_pre[j] : __ldg(g.res + (size_t)row * g.ld_res + col)) : 0.f;
       } else if (g.epi == RC_EPI_MASK_POS) {
-        v = (ok && __ldg(g.e_aux + (size_t)row * g.ld_e_aux + col) > 0.f) ? v : 0.f;
+        v = (ok && (e_early ? e_pre[j] : __ldg(g.e_aux + (size_t)row * g.ld_e_aux + col)) > 0.f) ? v : 0.f;
       }
       out[j] = v;
       if (BL == RC_B_COL && g.bits_out != nullptr) {

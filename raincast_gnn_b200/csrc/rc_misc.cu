@@ -31,8 +31,7 @@ __global__ void __launch_bounds__(32) adamw_tick_kernel(const AdamTickP p) {
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamP p) {
-  pdl_entry();
-  adamw_tile(p, blockIdx, gridDim);
+  adamw_tile(p, blockIdx, gridDim);        // (griddepcontrol.wait is its first statement)
 }
 
 // One batch of forecast dates out of a device-resident split: the three per-date blocks (node features, ensemble, targets)

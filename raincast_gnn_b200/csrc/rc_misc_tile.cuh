@@ -285,21 +285,23 @@ __device__ __forceinline__ void adamw_finish(long long* step, unsigned int n_cta
   }
 }
 
+// 128-bit accesses when the buffers allow it (the engine's flat buffers always do).  Nothing is read before the wait for
+// the previous kernel: two optimiser steps may follow each other directly, and the first one writes what the second reads.
 __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, const uint3 gdim) {
   float* __restrict__ param = p.param;
   const float* __restrict__ grad = p.grad;
   float* __restrict__ exp_avg = p.exp_avg;
   float* __restrict__ exp_avg_sq = p.exp_avg_sq;
   const long long* __restrict__ step = p.step;
-  long long n = p.n;
-  float lr = p.lr;
-  float beta1 = p.beta1;
-  float beta2 = p.beta2;
-  float eps = p.eps;
-  float weight_decay = p.weight_decay;
-  float grad_scale = p.grad_scale;
-  (void)bid; (void)gdim;
+  const long long n = p.n;
+  const float lr = p.lr, beta1 = p.beta1, beta2 = p.beta2, eps = p.eps, weight_decay = p.weight_decay, grad_scale = p.grad_scale;
 
+  const bool vec = ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+                     reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15u) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  const long long stride = (long long)gdim.x * 256;
+  const long long first = (long long)bid.x * 256 + threadIdx.x;
+  pdl_entry();
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0) {
     const double t = (double)(step[0] + 1);
@@ -309,15 +311,30 @@ __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, cons
   }
   __syncthreads();
   const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  for (long long i = (long long)bid.x * 256 + threadIdx.x; i < n; i += (long long)gdim.x * 256) {
-    const float g = grad[i] * grad_scale;
-    float p = param[i] * (1.0f - lr * weight_decay);
-    float m1 = exp_avg[i], v = exp_avg_sq[i];
-    m1 = m1 + (g - m1) * (1.0f - beta1);                 // lerp_
-    v = v * beta2 + (1.0f - beta2) * g * g;              // mul_ + addcmul_
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p = p - step_size * (m1 / denom);
-    param[i] = p; exp_avg[i] = m1; exp_avg_sq[i] = v;
+  auto update = [&](float g, float& pw, float& pm, float& pv) {
+    g *= grad_scale;
+    float q = pw * (1.0f - lr * weight_decay);
+    pm = pm + (g - pm) * (1.0f - beta1);                 // lerp_
+    pv = pv * beta2 + (1.0f - beta2) * g * g;            // mul_ + addcmul_
+    const float denom = sqrtf(pv) / bc2_sqrt + eps;
+    pw = q - step_size * (pm / denom);
+  };
+  for (long long i = first; i < n4; i += stride) {
+    float4 w = reinterpret_cast<const float4*>(param)[i], m1 = reinterpret_cast<const float4*>(exp_avg)[i],
+           v2 = reinterpret_cast<const float4*>(exp_avg_sq)[i];
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    update(g.x, w.x, m1.x, v2.x);
+    update(g.y, w.y, m1.y, v2.y);
+    update(g.z, w.z, m1.z, v2.z);
+    update(g.w, w.w, m1.w, v2.w);
+    reinterpret_cast<float4*>(param)[i] = w;
+    reinterpret_cast<float4*>(exp_avg)[i] = m1;
+    reinterpret_cast<float4*>(exp_avg_sq)[i] = v2;
+  }
+  for (long long i = 4 * n4 + first; i < n; i += stride) {       // unaligned buffers / the last n % 4 elements
+    float pw = param[i], pm = exp_avg[i], pv = exp_avg_sq[i];
+    update(grad[i], pw, pm, pv);
+    param[i] = pw; exp_avg[i] = pm; exp_avg_sq[i] = pv;
   }
   adamw_finish(p.step, gdim.x);
 }
