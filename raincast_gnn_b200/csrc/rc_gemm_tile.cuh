@@ -161,8 +161,9 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
     for (int it = 0; it < B_IT; ++it) {
       const int s = tid + it * kGemmThreads;
       const int row = s / B_F4_PER_ROW, c4 = (s % B_F4_PER_ROW) * 4;
-      if (BL == RC_B_COL) rb[it] = load_op4(g.b, bbase, ldb, n0 + row, k0 + c4, g.n, kk, bvec, !seg2);
-      else                rb[it] = load_op4(g.b, bbase, ldb, k0 + row, n0 + c4, kk, g.n, bvec, !seg2);
+      // (a B prologue only exists for weight-gradient GEMMs, A stored [r][i]: compiled out of the activation GEMMs)
+      if (BL == RC_B_COL) rb[it] = load_op4(g.b, bbase, ldb, n0 + row, k0 + c4, g.n, kk, bvec, AL == RC_A_RED && !seg2);
+      else                rb[it] = load_op4(g.b, bbase, ldb, k0 + row, n0 + c4, kk, g.n, bvec, AL == RC_A_RED && !seg2);
     }
   };
   auto load_tile = [&](int t) { load_a(t); load_b(t); };
@@ -295,7 +296,8 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
     __syncthreads();                  // the epilogue reuses the front of shared memory
   }
   int cur = 0;
-  for (int t = kWarpSplit ? t_end : t_beg; t < t_end; ++t) {
+  if constexpr (!kWarpSplit)          // (the warp-split instantiation never runs this loop: keep it out of its code image)
+  for (int t = t_beg; t < t_end; ++t) {
     const bool more = t + 1 < t_end;
     if (more) load_tile(t + 1);
     const float* as = As + cur * A_STAGE;
