@@ -469,6 +469,52 @@ def dp_check(dev, pg, rank, world, steps: int = 4):
     return out
 
 
+def dp_check_one_gpu(dev, ranks: int = 4, per_rank: int = 2):
+    """N = 1: data-parallel SEMANTICS carried by the bench line without a second GPU.  `ranks` micro-batches of `per_rank`
+    small station graphs go through the engine's emulated-rank step (per-rank BatchNorm statistics and valid-node means,
+    gradients summed in rank order, ONE AdamW step with grad_scale = 1/ranks: the arithmetic of rc_p2p_step) and through
+    the float64 oracle (independent passes from the same weights, mean of the gradients); reported: the worst relative
+    difference of the per-rank losses and of the mean gradient tensors (max-norm; the bias in front of BatchNorm, whose
+    true gradient is zero, on its weight's scale)."""
+    from oracle import model as om, pyg as opyg
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.pyg_compat import DataLoader
+    from raincast_gnn_b200.utils import synthetic as syn
+    from raincast_gnn_b200.utils.dataset import SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=ranks * per_rank, num_stations=40, members=11, feats=9, max_dist=200.0)
+    loader = list(DataLoader(ds, batch_size=per_rank))
+    kw = dict(MODEL_KW, in_channels=9, num_layers_gnn=2, optimizer_params={"lr": 1e-3})
+    ours = GNN(**kw)
+    sd = syn.seeded_state_dict(ours.state_dict(), seed=7)
+    ours.load_state_dict(sd)
+    ours.to(dev).train()
+    eng = TrainEngine(ours, loader[0].station_graph, loader[0].x.shape[0], 11, 9, lr=1e-3, use_cuda_graph=False)
+    losses, mean_grads = eng.step_emulated_ranks([(b.x, b.ensemble, b.y) for b in loader])
+    ref = om.GNN(**kw).double()
+    ref.load_state_dict({k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()})
+    ref.conv.force_float = False
+    ref.train()
+    acc = {k: torch.zeros_like(p) for k, p in ref.named_parameters()}
+    ref_losses = []
+    for b in loader:
+        d = opyg.Data(x=b.x.double(), ensemble=b.ensemble.double(), edge_index=b.edge_index, edge_attr=b.edge_attr.double(), y=b.y.double())
+        ref.zero_grad()
+        loss = ref.loss_fn.crps(ref(d), d.y)
+        loss.backward()
+        ref_losses.append(float(loss.detach()))
+        for k, p in ref.named_parameters():
+            acc[k] += p.grad
+    worst = 0.0
+    for k in acc:
+        want = acc[k] / ranks
+        scale = (acc[k[:-4] + "weight"] / ranks).abs().max().item() if k.endswith(".nn.0.bias") else want.abs().max().item()
+        worst = max(worst, (mean_grads[k].cpu().double() - want).abs().max().item() / max(scale, 1e-12))
+    lo = torch.tensor(ref_losses, dtype=torch.float64)
+    return {"mode": f"{ranks} ranks emulated on one GPU vs the float64 micro-batch oracle", "loss_max_rel_err": float(((losses.cpu() - lo).abs() / lo.abs()).max()),
+            "mean_gradient_max_rel_err": worst, "within_1e-5": bool(worst < 1e-5)}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -571,6 +617,11 @@ def run_b200(args):
     if world > 1:
         try:
             line["dp_check"] = dp_check(dev, pg, rank, world)
+        except Exception as exc:
+            line["dp_check"] = {"error": repr(exc)}
+    else:
+        try:
+            line["dp_check"] = dp_check_one_gpu(dev)
         except Exception as exc:
             line["dp_check"] = {"error": repr(exc)}
     if rank == 0:
