@@ -131,6 +131,8 @@ extern "C" int rc_gemm_run(const rc_gemm* g, void* stream) {
       return fail(RC_ERR_ARG, "rc_gemm_run: RC_OP_GINE_AGGR needs 4 | k, 4 | ld and 16-byte aligned x, w_edge, b_edge, a_out");
   }
   if (g->b.op == RC_OP_GINE_AGGR) return fail(RC_ERR_ARG, "rc_gemm_run: RC_OP_GINE_AGGR is an A-operand prologue");
+  if (g->a_layout == RC_A_RED && (g->epi != RC_EPI_NONE || g->bits_out))
+    return fail(RC_ERR_ARG, "rc_gemm_run: weight-gradient GEMMs (A stored [r][i]) take RC_EPI_NONE and no bits_out");
   if (g->b.op != RC_OP_NONE && g->a_layout != RC_A_RED)
     return fail(RC_ERR_ARG, "rc_gemm_run: a B-operand prologue exists for weight-gradient GEMMs only (A stored [r][i])");
   if (g->m == 0 || g->n == 0) return RC_OK;

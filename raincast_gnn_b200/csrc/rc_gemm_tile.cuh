@@ -206,26 +206,28 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
       if (row < g.m && col < g.n) e_pre[j] = __ldg(src + (size_t)row * ld + col);
     }
   }
-  if (p.b_early && t_beg < t_end) {
-    load_b(t_beg);
-    pdl_entry();
-    load_a(t_beg);
-    store_tile(0);
-  } else {
-    pdl_entry();
-    if (t_beg < t_end) {
-      load_tile(t_beg);
+  constexpr bool kWarpSplit = (RM == 1 && kRK == 128 && AL == RC_A_ROW);
+  if constexpr (kWarpSplit) {
+    if (p.b_early && t_beg < t_end) {
+      load_b(t_beg);
+      pdl_entry();
+      load_a(t_beg);
       store_tile(0);
+    } else {
+      pdl_entry();
+      if (t_beg < t_end) {
+        load_tile(t_beg);
+        store_tile(0);
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
   // Warp-split reduction for the latency-bound shape (8-row tile, 128-long slices - every Linear of the reference
   // step at B = 8 graphs): warp w takes reduction indices [16 w, 16 w + 16) of every slice for ALL eight rows instead
   // of the whole reduction for one row, so that the CTA reads the 64 KB weight tile from shared memory
   // once instead of eight times (the shared-memory pipe, not FFMA, bounded this shape); the eight partial
   // [8 x 128] tiles meet in shared memory and warp w sums row w in a fixed order.
-  constexpr bool kWarpSplit = (RM == 1 && kRK == 128 && AL == RC_A_ROW);
-  if (kWarpSplit) {
+  if constexpr (kWarpSplit) {
     float acc8[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -296,14 +298,25 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
     __syncthreads();                  // the epilogue reuses the front of shared memory
   }
   int cur = 0;
-  if constexpr (!kWarpSplit)          // (the warp-split instantiation never runs this loop: keep it out of its code image)
-  for (int t = t_beg; t < t_end; ++t) {
+  // (the warp-split instantiation never runs this loop: it is kept out of its code image.)  ONE site for the operand
+  // loads: the pass t = t_beg - 1 only fetches - with the wait for the previous kernel behind an early B fetch - so that
+  // the loaders (sixteen-fold unrolled, with their prologues) exist once in the kernel instead of twice: these kernels
+  // start with a cold instruction cache and their time follows their code size.
+  if constexpr (!kWarpSplit)
+#pragma unroll 1
+  for (int t = t_beg - 1; t < t_end; ++t) {
     const bool more = t + 1 < t_end;
-    if (more) load_tile(t + 1);
+    const bool first = t == t_beg - 1;
+    const bool early = p.b_early && more;
+    if (first && !early) pdl_entry();
+    if (more) load_b(t + 1);
+    if (first && early) pdl_entry();
+    if (more) load_a(t + 1);
     const float* as = As + cur * A_STAGE;
     const float* bs = Bs + cur * B_STAGE;
     // 8 reduction quads per unrolled body: the long-slice variant (32 quads) stays small enough for the instruction
     // cache, which is cold at every launch of a step made of ~75 different small kernels
+    if (!first)
 #pragma unroll 8
     for (int r4 = 0; r4 < kRK / 4; ++r4) {
       float a[RM][4], b[4][4];   // a[i][rr], b[rr][j]
@@ -349,9 +362,9 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][rr], b[rr][j], acc[i][j]);
     }
-    if (more) store_tile(cur ^ 1);
+    if (more) store_tile(first ? 0 : (cur ^ 1));
     __syncthreads();
-    cur ^= 1;
+    if (!first) cur ^= 1;
   }
 
   // ------------------------------------------------------------------------------------------ epilogue
@@ -373,7 +386,8 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] += bias_v[j];
 
-  if (g.epi == RC_EPI_BN_STATS || g.epi == RC_EPI_BN_RELU_BWD) {
+  // (weight-gradient GEMMs, A stored [r][i], have no epilogue beyond the store: the variants below are compiled out of them)
+  if (AL != RC_A_RED && (g.epi == RC_EPI_BN_STATS || g.epi == RC_EPI_BN_RELU_BWD)) {
     // per-column reductions over the rows of this tile: warp partials -> smem -> 128 column threads
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     if (g.epi == RC_EPI_BN_RELU_BWD) {
@@ -459,7 +473,8 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
       const bool ok = rok && col < g.n;
       float v = acc[i][j];
       bool pos = v > 0.f;
-      if (g.epi == RC_EPI_RELU) {
+      if (AL == RC_A_RED) {
+      } else if (g.epi == RC_EPI_RELU) {
         v = fmaxf(v, 0.f);
       } else if (g.epi == RC_EPI_RELU_RES) {
         v = (ok ? (e_early ? e_pre[j] : __ldg(g.res + (size_t)row * g.ld_res + col)) : 0.f) + fmaxf(v, 0.f);
@@ -469,7 +484,7 @@ __device__ __forceinline__ void gemm_tile(const GemmP& p, const uint3 bid, float
         v = (ok && (e_early ? e_pre[j] : __ldg(g.e_aux + (size_t)row * g.ld_e_aux + col)) > 0.f) ? v : 0.f;
       }
       out[j] = v;
-      if (BL == RC_B_COL && g.bits_out != nullptr) {
+      if (AL != RC_A_RED && BL == RC_B_COL && g.bits_out != nullptr) {
         const unsigned word = __ballot_sync(0xffffffffu, ok && pos);   // lane l <-> column 32*j + l of the tile
         if (lane == 0 && rok && n0 + 32 * j < g.n) g.bits_out[(size_t)row * g.ld_bits_out + (n0 >> 5) + j] = word;
       }
