@@ -93,6 +93,7 @@ class TrainEngine:
         self._blocks = self._bind(model)
         self.use_cuda_graph = use_cuda_graph
         self._side = torch.cuda.Stream(device=dev)      # weight-gradient work overlaps the data-gradient chain
+        self._side2 = torch.cuda.Stream(device=dev) if os.environ.get("RC_SIDE_ALT", "1") != "0" else None   # tail of backward
         # input prefetch: the next batch travels host -> staging buffers on a copy stream while the current step runs
         # In graph mode the staging buffers are a second input set with its own captured graph (same kernels, same
         # pool): taking the prefetched batch is a flip, not a copy.  Other modes copy device -> device.
@@ -177,12 +178,12 @@ class TrainEngine:
         """One whole training step on the current stream (+ the side stream): forward, CRPS, backward and - unless the
         gradients travel through NCCL - the gradient exchange, AdamW and the running loss sum.  This is what the CUDA
         graph holds."""
-        K.SIDE.stream = self._side
+        K.SIDE.stream, K.SIDE.alt = self._side, self._side2
         try:
             self._fwd_bwd_body()
             K.join_side()
         finally:
-            K.SIDE.stream = None
+            K.SIDE.stream = K.SIDE.alt = None
         if self._opt_in_graph:
             self._optimizer()
             self.loss_sum.add_(self.loss)
@@ -390,12 +391,12 @@ class TrainEngine:
         losses = []
         for x, ens, y in batches:
             self.load_batch(x, ens, y)
-            K.SIDE.stream = self._side
+            K.SIDE.stream, K.SIDE.alt = self._side, self._side2
             try:
                 self._fwd_bwd_body()
                 K.join_side()
             finally:
-                K.SIDE.stream = None
+                K.SIDE.stream = K.SIDE.alt = None
             total += self.flat_g
             losses.append(self.loss.clone())
         _lib.check(_lib.lib().rc_adamw_step(self.flat_p.data_ptr(), total.data_ptr(), self.exp_avg.data_ptr(),

@@ -39,6 +39,8 @@ class _Side:
     their reductions).  Enabled by the graphed engine: inside a CUDA-graph capture the event waits become graph
     edges, so the weight-gradient GEMMs run concurrently with the data-gradient chain on otherwise idle SMs."""
     stream = None
+    alt = None             # a third stream for the tail of backward (DeepSets / dim_red weight gradients), see on_side(alt=True)
+    alt_dirty = False      # work was issued on `alt` that the next reduction / join has to wait for
     keep: list = []
 
 
@@ -71,18 +73,33 @@ def _new_like(ref):
 
 
 @contextlib.contextmanager
-def on_side(*inputs):
+def on_side(*inputs, alt: bool = False):
     """Run the enclosed launches on the side stream, ordered after everything issued so far on the current stream.
-    `inputs` (tensors produced on the main stream and read here) are kept alive until join_side()."""
+    `inputs` (tensors produced on the main stream and read here) are kept alive until join_side().
+    alt=True: on the second side stream when the engine provides one.  The weight-gradient GEMMs at the END of backward
+    (dim_red, DeepSets) are the tail of the step - the optimiser waits for them - and independent of one another:
+    alternating two streams overlaps their launch-to-finish latencies.  GradSink.flush / join_side wait for both."""
     if SIDE.stream is None:
         yield
         return
+    s = SIDE.alt if (alt and SIDE.alt is not None) else SIDE.stream
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream())
-    SIDE.stream.wait_event(ev)
+    s.wait_event(ev)
     SIDE.keep.extend(inputs)
-    with torch.cuda.stream(SIDE.stream):
+    if s is SIDE.alt:
+        SIDE.alt_dirty = True
+    with torch.cuda.stream(s):
         yield
+
+
+def _wait_alt():
+    """Order the current stream behind the second side stream's work (before a reduction of partials it produced)."""
+    if SIDE.alt is not None and SIDE.alt_dirty and torch.cuda.current_stream() != SIDE.alt:
+        ev = torch.cuda.Event()
+        ev.record(SIDE.alt)
+        torch.cuda.current_stream().wait_event(ev)
+        SIDE.alt_dirty = False
 
 
 def join_side():
@@ -91,6 +108,7 @@ def join_side():
     ev = torch.cuda.Event()
     ev.record(SIDE.stream)
     torch.cuda.current_stream().wait_event(ev)
+    _wait_alt()
     SIDE.keep.clear()
 
 
@@ -178,9 +196,14 @@ class GradSink:
 
     def flush(self):
         if self.segs:
+            _wait_alt()
             arr = (_lib.rc_reduce_seg * len(self.segs))(*self.segs)
             _lib.check(_lib.lib().rc_reduce_segments(arr, len(self.segs), torch.cuda.current_stream(self.device).cuda_stream),
                        "rc_reduce_segments")
+        if SIDE.stream is not None:
+            # partials written on one side stream and reduced on another: they must not go back to the allocator (and be
+            # handed to a later launch on the stream that wrote them) before the step's streams have been joined
+            SIDE.keep.extend(self.keep)
         self.segs, self.keep = [], []
 
 
@@ -237,7 +260,7 @@ def deepsets_bwd(P, saved, d_emb, G, mask_out=None):
         linear_bwd_weight(operand(d_emb, ho), operand(r1, h), m, ho, h, G["rho2_w"], G["rho2_b"], sink)
     d_r1 = linear_bwd_data(d_emb, P["rho2_w"], mask_pos=r1)
     # rho[0]
-    with on_side(d_r1):
+    with on_side(d_r1, alt=True):
         linear_bwd_weight(operand(d_r1, h), operand(s2, h), m, h, h, G["rho0_w"], G["rho0_b"], sink)
     d_s2 = linear_bwd_data(d_r1, P["rho0_w"])
     # phi[2] (after the pool): bias gradient carries the member count
@@ -329,8 +352,9 @@ def dimred_bwd(P, saved, dy, G):
     n, ldw = w.shape
     sink = GradSink(x.device)
     dw = G["dimred_w"]
-    with on_side(dy):
+    with on_side(dy, alt=True):
         linear_bwd_weight(operand(dy, n), operand(x, f), m, n, f, dw[:, :f], G["dimred_b"], sink, dw_ld=ldw)
+    with on_side(dy):
         linear_bwd_weight(operand(dy, n), operand(emb, h_in), m, n, h_in, dw[:, f:], None, sink, dw_ld=ldw)
         sink.flush()
     pack = _dimred_pack(P, f)
