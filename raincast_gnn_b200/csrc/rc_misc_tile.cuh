@@ -285,6 +285,22 @@ __device__ __forceinline__ void adamw_finish(long long* step, unsigned int n_cta
   }
 }
 
+// One element of torch.optim.AdamW's update (decoupled decay, lerp_, mul_ + addcmul_, bias corrections as torch computes
+// them), with every rounding spelled out: rc_adamw_step and the peer-memory exchange kernel (rc_p2p_step) must produce
+// the same bits from the same summed gradient - the data-parallel check compares their loss trajectories for equality -
+// and that cannot be left to how the compiler contracts two differently shaped loops.
+struct AdamCoef {
+  float grad_scale, decay, one_m_b1, beta2, one_m_b2, bc2_sqrt, eps, step_size;
+};
+__device__ __forceinline__ void adam_update(const AdamCoef& c, float g, float& w, float& m, float& v) {
+  g = __fmul_rn(g, c.grad_scale);
+  const float q = __fmul_rn(w, c.decay);
+  m = __fmaf_rn(__fsub_rn(g, m), c.one_m_b1, m);
+  v = __fmaf_rn(__fmul_rn(c.one_m_b2, g), g, __fmul_rn(v, c.beta2));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt), c.eps);
+  w = __fmaf_rn(-c.step_size, __fdiv_rn(m, denom), q);
+}
+
 // 128-bit accesses when the buffers allow it (the engine's flat buffers always do).  Nothing is read before the wait for
 // the previous kernel: two optimiser steps may follow each other directly, and the first one writes what the second reads.
 __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, const uint3 gdim) {
@@ -310,15 +326,8 @@ __device__ __forceinline__ void adamw_tile(const AdamP& p, const uint3 bid, cons
     s_bc2_sqrt = (float)sqrt(bc2);
   }
   __syncthreads();
-  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  auto update = [&](float g, float& pw, float& pm, float& pv) {
-    g *= grad_scale;
-    float q = pw * (1.0f - lr * weight_decay);
-    pm = pm + (g - pm) * (1.0f - beta1);                 // lerp_
-    pv = pv * beta2 + (1.0f - beta2) * g * g;            // mul_ + addcmul_
-    const float denom = sqrtf(pv) / bc2_sqrt + eps;
-    pw = q - step_size * (pm / denom);
-  };
+  const AdamCoef c{grad_scale, 1.0f - lr * weight_decay, 1.0f - beta1, beta2, 1.0f - beta2, s_bc2_sqrt, eps, s_step_size};
+  auto update = [&](float g, float& pw, float& pm, float& pv) { adam_update(c, g, pw, pm, pv); };
   for (long long i = first; i < n4; i += stride) {
     float4 w = reinterpret_cast<const float4*>(param)[i], m1 = reinterpret_cast<const float4*>(exp_avg)[i],
            v2 = reinterpret_cast<const float4*>(exp_avg_sq)[i];

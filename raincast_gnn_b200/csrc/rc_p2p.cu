@@ -108,16 +108,11 @@ __global__ void __launch_bounds__(256) p2p_adamw_kernel(const P2pAdamP p) {
     }
     float4 w = reinterpret_cast<float4*>(a.param)[i], m1 = reinterpret_cast<float4*>(a.exp_avg)[i],
            v2 = reinterpret_cast<float4*>(a.exp_avg_sq)[i];
-    float* gp = &g.x; float* wp = &w.x; float* mp = &m1.x; float* vp = &v2.x;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gj = gp[j] * a.grad_scale;
-      float pj = wp[j] * decay;
-      mp[j] = mp[j] + (gj - mp[j]) * one_m_b1;                 // lerp_
-      vp[j] = vp[j] * a.beta2 + one_m_b2 * gj * gj;            // mul_ + addcmul_
-      const float denom = sqrtf(vp[j]) / bc2_sqrt + a.eps;
-      wp[j] = pj - step_size * (mp[j] / denom);
-    }
+    const AdamCoef c{a.grad_scale, decay, one_m_b1, a.beta2, one_m_b2, bc2_sqrt, a.eps, step_size};
+    adam_update(c, g.x, w.x, m1.x, v2.x);
+    adam_update(c, g.y, w.y, m1.y, v2.y);
+    adam_update(c, g.z, w.z, m1.z, v2.z);
+    adam_update(c, g.w, w.w, m1.w, v2.w);
     reinterpret_cast<float4*>(a.param)[i] = w;
     reinterpret_cast<float4*>(a.exp_avg)[i] = m1;
     reinterpret_cast<float4*>(a.exp_avg_sq)[i] = v2;
@@ -229,16 +224,11 @@ __global__ void __launch_bounds__(256) p2p_step_kernel(const P2pAdamP p, int* co
       if (s_flag && threadIdx.x < p.world) flag_publish(flags[threadIdx.x] + kMaxPeers + rank, ep);
     }
     if (i < n4) {
-      float* gp = &g.x; float* wp = &w.x; float* mp = &m1.x; float* vp = &v2.x;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float gj = gp[j] * a.grad_scale;
-        float pj = wp[j] * decay;
-        mp[j] = mp[j] + (gj - mp[j]) * one_m_b1;                 // lerp_
-        vp[j] = vp[j] * a.beta2 + one_m_b2 * gj * gj;            // mul_ + addcmul_
-        const float denom = sqrtf(vp[j]) / bc2_sqrt + a.eps;
-        wp[j] = pj - step_size * (mp[j] / denom);
-      }
+      const AdamCoef c{a.grad_scale, decay, one_m_b1, a.beta2, one_m_b2, bc2_sqrt, a.eps, step_size};
+      adam_update(c, g.x, w.x, m1.x, v2.x);
+      adam_update(c, g.y, w.y, m1.y, v2.y);
+      adam_update(c, g.z, w.z, m1.z, v2.z);
+      adam_update(c, g.w, w.w, m1.w, v2.w);
       reinterpret_cast<float4*>(a.param)[i] = w;
       reinterpret_cast<float4*>(a.exp_avg)[i] = m1;
       reinterpret_cast<float4*>(a.exp_avg_sq)[i] = v2;
