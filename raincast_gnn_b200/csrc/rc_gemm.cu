@@ -81,7 +81,10 @@ static int choose_rm(const rc_gemm* g) {
   const int cands[4] = {8, 4, 2, 1};
   for (int c = 0; c < 4; ++c) {
     const long long ctas = (long long)ceil_div(g->m > 0 ? g->m : 1, 8 * cands[c]) * col_tiles * sp;
-    if (ctas >= kNumSMs) return cands[c];
+    // weight-gradient GEMMs run beside the data-gradient chain and cost it through the issue slots they take: 124 CTAs of
+    // 32 output rows did better than 248 of 16 at the reference shape (250.5 vs 254.7 us per step; 8 rows: 284, 64 rows: 272)
+    const long long enough = g->a_layout == RC_A_RED ? 96 : kNumSMs;
+    if (ctas >= enough) return cands[c];
   }
   return 1;
 }
