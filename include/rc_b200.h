@@ -307,6 +307,19 @@ int rc_crps_fwd_bwd(const float* pred, const float* y, float* d_pred /* nullable
                     int32_t* n_valid, int num_nodes, int kind, int raw_input, float u_fixed, float xi, float t,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Head Linear (models/gnn.py:123,139: `aggr`, H -> C) + links + CRPS + their backward in ONE launch, for batches of up to
+ * 16 384 nodes and H = 128 or 256 (rc_head_crps_blocks returns 0 when it does not apply: use rc_gemm_run + rc_crps_fwd_bwd).
+ *   h [M][H] last hidden state, w [C][H], b [C] (C = kind + 2), y [M] targets (NaN = missing)
+ *   d_h [M][H]           gradient of the mean CRPS w.r.t. h
+ *   partials [blocks][C*H + C]   per-CTA partial d w (row-major [C][H]) followed by d b: sum over blocks (rc_reduce_segments)
+ *   loss_partials [blocks] float64 scratch; loss_out float64[1] = mean over valid nodes; n_valid int32[1]
+ * y and w are read BEFORE the kernel waits for the launch in front of it on the stream (programmatic dependent launch):
+ * that launch must not write them. */
+int rc_head_crps_blocks(int num_nodes, int hidden);
+int rc_head_crps_fwd_bwd(const float* h, const float* w, const float* b, const float* y, float* d_h, float* partials,
+                         double* loss_partials, double* loss_out, int32_t* n_valid, int num_nodes, int hidden, int kind,
+                         float u_fixed, float xi, float t, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimiser (train.py:66-69,185: torch.optim.AdamW defaults) on flat parameter / gradient buffers
  * ---------------------------------------------------------------------------------------------- */

@@ -97,6 +97,8 @@ def _declare(lib):
         "rc_postprocess_bwd": (i, [p, p, p, i, i, p]),
         "rc_crps_workspace": (sz, [i]),
         "rc_crps_fwd_bwd": (i, [p, p, p, p, p, i, i, i, f, f, f, p, sz, p]),
+        "rc_head_crps_blocks": (i, [i, i]),
+        "rc_head_crps_fwd_bwd": (i, [p, p, p, p, p, p, p, p, p, i, i, i, f, f, f, p]),
         "rc_adamw_step": (i, [p, p, p, p, p, ll, f, f, f, f, f, f, p]),
         "rc_gather_dates": (i, [p, p, p, p, i, i, ll, ll, ll, p, p, p, p, p]),
         "rc_p2p_barrier": (i, [p, p, i, i, i, p, p]),

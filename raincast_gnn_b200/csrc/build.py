@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["rc_core.cu", "rc_graph.cu", "rc_gine.cu", "rc_gine_wide.cu", "rc_gine_tiled.cu", "rc_tiles.cu", "rc_gemm.cu", "rc_gemm_tc.cu", "rc_deepsets.cu", "rc_deepsets_tc.cu", "rc_deepsets_tc_bwd.cu", "rc_crps.cu", "rc_misc.cu", "rc_p2p.cu", "rc_debug.cu"]
+SOURCES = ["rc_core.cu", "rc_graph.cu", "rc_gine.cu", "rc_gine_wide.cu", "rc_gine_tiled.cu", "rc_tiles.cu", "rc_gemm.cu", "rc_gemm_tc.cu", "rc_deepsets.cu", "rc_deepsets_tc.cu", "rc_deepsets_tc_bwd.cu", "rc_crps.cu", "rc_head.cu", "rc_misc.cu", "rc_p2p.cu", "rc_debug.cu"]
 HEADERS = ["rc_common.cuh", "rc_umma.cuh", "rc_crps_node.cuh", "rc_gemm_tile.cuh", "rc_gine_tile.cuh", "rc_deepsets_tile.cuh",
            "rc_crps_tile.cuh", "rc_misc_tile.cuh", os.path.join(ROOT, "include", "rc_b200.h")]
 LIB = os.path.join(HERE, "librc_b200.so")

@@ -44,6 +44,9 @@ def _flatten_into(tensors, flat):
     return views
 
 
+FUSE_HEAD = os.environ.get("RC_FUSE_HEAD", "1") != "0"      # 0: head GEMM, CRPS kernel and head backward as separate launches (A/B, tests)
+
+
 class TrainEngine:
     def __init__(self, model, graph: StationGraph, num_nodes: int, members: int, feats: int, *, lr: float = 1e-4,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None,
@@ -201,10 +204,14 @@ class TrainEngine:
             h, s = K.gine_layer_fwd(Pl, h, self.graph, first=(i == 0), training=True)
             saved.append(s)
         Ph, Gh = blk["head"]
-        raw, s_h = K.head_fwd(Ph, h)
-        _, d_raw, _ = K.crps_fwd_bwd(raw, self.y, self.kind, raw_input=True, u=self.u_fixed, xi=self.xi, t=self.t,
-                                     loss_out=self.loss)
-        d = K.head_bwd(Ph, s_h, d_raw, Gh)
+        if FUSE_HEAD and K.head_crps_blocks(h.shape[0], h.shape[1]) > 0:
+            # head Linear + links + CRPS + their backward: one launch instead of three on the chain and one beside it
+            _, d, _ = K.head_crps_fwd_bwd(Ph, h, self.y, self.kind, Gh, u=self.u_fixed, xi=self.xi, t=self.t, loss_out=self.loss)
+        else:
+            raw, s_h = K.head_fwd(Ph, h)
+            _, d_raw, _ = K.crps_fwd_bwd(raw, self.y, self.kind, raw_input=True, u=self.u_fixed, xi=self.xi, t=self.t,
+                                         loss_out=self.loss)
+            d = K.head_bwd(Ph, s_h, d_raw, Gh)
         for i in reversed(range(len(blk["layers"]))):
             Pl, Gl = blk["layers"][i]
             d = K.gine_layer_bwd(Pl, saved[i], self.graph, d, Gl, first=(i == 0), training=True)

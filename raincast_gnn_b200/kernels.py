@@ -535,6 +535,34 @@ def head_bwd(P, saved, d_raw, G):
     return linear_bwd_data(d_raw, P["aggr_w"])
 
 
+def head_crps_blocks(m: int, hidden: int) -> int:
+    """CTAs of the fused head + CRPS kernel, 0 when it does not apply (large batches, other widths)."""
+    return int(_lib.lib().rc_head_crps_blocks(int(m), int(hidden)))
+
+
+def head_crps_fwd_bwd(P, x, y, kind, G, *, u=0.0, xi=0.5, t=5.0, loss_out=None):
+    """Head Linear + links + CRPS + backward in ONE launch (small batches): returns (loss float64[1], d_x, n_valid).
+    The weight / bias gradient partials are reduced on the side stream."""
+    m, h = x.shape
+    c = P["aggr_w"].shape[0]
+    dev = x.device
+    nb = head_crps_blocks(m, h)
+    d_x = _new((m, h), torch.float32, dev)
+    part = _new((nb, c * h + c), torch.float32, dev)
+    lp = _new((nb,), torch.float64, dev)
+    loss = loss_out if loss_out is not None else _new((1,), torch.float64, dev)
+    n_valid = _new((1,), torch.int32, dev)
+    _lib.check(_lib.lib().rc_head_crps_fwd_bwd(x.data_ptr(), P["aggr_w"].data_ptr(), P["aggr_b"].data_ptr(), y.data_ptr(), d_x.data_ptr(),
+                                               part.data_ptr(), lp.data_ptr(), loss.data_ptr(), n_valid.data_ptr(), m, h, kind,
+                                               float(u), float(xi), float(t), _stream(x)), "rc_head_crps_fwd_bwd")
+    sink = GradSink(dev)
+    sink.add(part, G["aggr_w"], c * h + c, nb, c * h)
+    sink.add(part.reshape(-1)[c * h:], G["aggr_b"], c * h + c, nb, c)
+    with on_side(part, lp):
+        sink.flush()
+    return loss, d_x, n_valid
+
+
 # --------------------------------------------------------------------------------------------- links + CRPS
 def postprocess_fwd(raw, kind):
     post = _new_like(raw)

@@ -588,3 +588,49 @@ def test_gine_tiled_irregular_multigraph(dev, h, max_src, max_block):
     sg = sg.to(dev)
     sg.__dict__["_tiles"] = {"pair": (fwd.to(dev), bwd.to(dev))}
     _tiled_vs_untiled(dev, sg, m, h, seed=3 * h)
+
+
+# ------------------------------------------------------------------------------------------------ fused head + CRPS
+@pytest.mark.parametrize("kind,c", [(3, 5), (2, 4), (1, 3), (0, 2)])
+@pytest.mark.parametrize("m,h", [(976, 128), (61, 128), (1003, 256)])
+def test_head_crps_fused_matches_the_three_kernel_path(dev, kind, c, m, h):
+    """rc_head_crps_fwd_bwd (head Linear + links + CRPS + backward in one launch) against rc_gemm_run + rc_crps_fwd_bwd +
+    the head's backward GEMMs, and against float64 for the loss: same valid count, loss, d h, d W, d b."""
+    from raincast_gnn_b200 import kernels as K
+    from raincast_gnn_b200.utils import synthetic as syn
+    g = torch.Generator().manual_seed(100 * kind + m)
+    x = torch.randn(m, h, generator=g).to(dev)
+    w = (torch.randn(c, h, generator=g) / h ** 0.5).to(dev)
+    b = (torch.randn(c, generator=g) * 0.1).to(dev)
+    y = syn.log_precip_targets(m, seed=kind + 1).to(dev)
+    y[::17] = float("nan")
+    P = {"aggr_w": w, "aggr_b": b}
+    assert K.head_crps_blocks(m, h) == -(-m // 8)
+    assert K.head_crps_blocks(20000, h) == 0 and K.head_crps_blocks(m, 512) == 0
+    # three-kernel path
+    G1 = {"aggr_w": torch.empty_like(w), "aggr_b": torch.empty_like(b)}
+    raw, s_h = K.head_fwd(P, x)
+    loss1, d_raw, nv1 = K.crps_fwd_bwd(raw, y, kind, raw_input=True, u=1.71, xi=0.5, t=5.0)
+    d1 = K.head_bwd(P, s_h, d_raw, G1)
+    # one kernel
+    G2 = {"aggr_w": torch.full_like(w, float("nan")), "aggr_b": torch.full_like(b, float("nan"))}
+    loss2, d2, nv2 = K.head_crps_fwd_bwd(P, x, y, kind, G2, u=1.71, xi=0.5, t=5.0)
+    torch.cuda.synchronize()
+    assert int(nv2) == int(nv1) == int((~torch.isnan(y)).sum())
+    assert abs(loss2.item() - loss1.item()) < 1e-6 * abs(loss1.item())
+    assert rel_err(_np(d2), _np(d1)) < TOL
+    assert rel_err(_np(G2["aggr_w"]), _np(G1["aggr_w"])) < TOL
+    assert rel_err(_np(G2["aggr_b"]), _np(G1["aggr_b"])) < TOL
+    # the loss against float64 links + CRPS of the float64 head output
+    from oracle import losses
+    raw64 = x.double().cpu() @ w.double().cpu().T + b.double().cpu()
+    name, gu = {3: ("MixedLoss", "True"), 2: ("MixedLoss", "False"), 1: ("MixedNormalCRPS", "False"), 0: ("NormalCRPS", "False")}[kind]
+    pred = losses.postprocess(raw64, name, gu)
+    y64 = y.double().cpu()
+    if kind >= 2:
+        want = losses.mixed_loss_crps(pred, y64, grad_u=(kind == 3), xi=0.5, u=None if kind == 3 else 1.71)
+    elif kind == 1:
+        want = losses.mixed_normal_crps(pred, y64)
+    else:
+        want = losses.normal_crps(pred, y64)
+    assert abs(loss2.item() - want.item()) < TOL * abs(want.item())
