@@ -64,41 +64,52 @@ def _graph_on(g: StationGraph, device) -> StationGraph:
 
 class Batch(Data):
     _GRAPH_CACHE: dict = {}
+    pin_outputs = False        # collate node tensors straight into pinned host memory (set by train.run_epoch_engine while it runs)
 
     @classmethod
     def from_data_list(cls, items):
+        """torch_geometric.data.Batch.from_data_list for the attributes the reference uses (utils/data.py:287-340): node
+        tensors concatenated, `edge_index` offset per graph, `batch` / `ptr`.  With the reference's static station graph
+        (every item shares ONE edge_index / edge_attr tensor, utils/data.py:300) the collated edge tensors, `batch`, `ptr`
+        and the CSR layout are the same for every batch of that size: they are built once and shared (read-only) by the
+        batches - per step only x / ensemble / y are concatenated, into pinned memory when `pin_outputs` is set."""
         out = cls()
         counts = [d.num_nodes for d in items]
+        e0, a0 = getattr(items[0], "edge_index", None), getattr(items[0], "edge_attr", None)
+        shared = (e0 is not None and a0 is not None and len(set(counts)) == 1 and
+                  all(getattr(d, "edge_index", None) is e0 and getattr(d, "edge_attr", None) is a0 for d in items))
+        key = (e0.data_ptr(), a0.data_ptr(), e0._version, len(items), counts[0]) if shared else None
+        hit = cls._GRAPH_CACHE.get(key) if key is not None else None
         offs = [0]
         for c in counts:
             offs.append(offs[-1] + c)
+        pin = cls.pin_outputs and torch.cuda.is_available()
         for k in items[0].keys():
             vals = [getattr(d, k) for d in items]
             if not torch.is_tensor(vals[0]):
                 setattr(out, k, vals)
+            elif hit is not None and k in ("edge_index", "edge_attr"):
+                setattr(out, k, hit[3][k])
             elif "index" in k:
                 setattr(out, k, torch.cat([v + o for v, o in zip(vals, offs)], dim=-1))
+            elif pin and vals[0].device.type == "cpu":
+                shape = (sum(v.shape[0] for v in vals),) + tuple(vals[0].shape[1:])
+                buf = torch.empty(shape, dtype=vals[0].dtype, pin_memory=True)
+                setattr(out, k, torch.cat(vals, dim=0, out=buf))
             else:
                 setattr(out, k, torch.cat(vals, dim=0))
+        if hit is not None:
+            out.batch, out.ptr, out.station_graph = hit[3]["batch"], hit[3]["ptr"], hit[0]
+            return out
         out.batch = torch.repeat_interleave(torch.arange(len(items)), torch.tensor(counts))
         out.ptr = torch.tensor(offs, dtype=torch.long)
-        out.station_graph = cls._station_graph(items, out, counts)
-        return out
-
-    @classmethod
-    def _station_graph(cls, items, out, counts):
-        # static graph (utils/data.py:300): every item shares the same edge tensors -> one layout per batch size
-        e0, a0 = items[0].edge_index, items[0].edge_attr
-        shared = all(d.edge_index is e0 and d.edge_attr is a0 for d in items) and len(set(counts)) == 1
-        key = (e0.data_ptr(), a0.data_ptr(), e0._version, len(items), counts[0]) if shared else None
-        if key is not None and key in cls._GRAPH_CACHE:
-            return cls._GRAPH_CACHE[key][0]
         g = build_station_graph(out.edge_index, out.edge_attr, int(out.x.shape[0]))
         if key is not None:
             if len(cls._GRAPH_CACHE) >= 64:
                 cls._GRAPH_CACHE.pop(next(iter(cls._GRAPH_CACHE)))
-            cls._GRAPH_CACHE[key] = (g, e0, a0)
-        return g
+            cls._GRAPH_CACHE[key] = (g, e0, a0, {"edge_index": out.edge_index, "edge_attr": out.edge_attr, "batch": out.batch, "ptr": out.ptr})
+        out.station_graph = g
+        return out
 
 
 class DataLoader:

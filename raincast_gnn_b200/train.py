@@ -85,6 +85,15 @@ def run_epoch_autograd(model, loader, optimizer, device) -> float:
 def run_epoch_engine(engine: TrainEngine, loader) -> float:
     """The same pass through the captured step: the next batch's H2D copy of x / ensemble / y runs on a copy stream
     while the current step replays, then (all-reduce,) fused AdamW."""
+    from .pyg_compat.data import Batch
+    was_pinning, Batch.pin_outputs = Batch.pin_outputs, torch.cuda.is_available()   # collate x / ensemble / y straight into pinned memory
+    try:
+        return _run_epoch_engine(engine, loader)
+    finally:
+        Batch.pin_outputs = was_pinning
+
+
+def _run_epoch_engine(engine: TrainEngine, loader) -> float:
     engine.loss_sum.zero_()
     done = 0
     pinned = torch.cuda.is_available()
