@@ -11,12 +11,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-def test_peer_memory_exchange_matches_nccl():
+@pytest.mark.parametrize("strict_flags", ["0", "1"])
+def test_peer_memory_exchange_matches_nccl(strict_flags):
     """rc_p2p_step (gradients summed straight from the peers' memory, in rank order, inside the AdamW kernel) against one
-    NCCL all-reduce + rc_adamw_step: same loss trajectories to 1e-5, bit-identical replicas on every rank."""
+    NCCL all-reduce + rc_adamw_step: same loss trajectories to 1e-5, bit-identical replicas on every rank - with the
+    default flag protocol (device-scope fences, rc_p2p_flag_scope(1)) and with release / acquire at system scope."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    env = dict(os.environ, NCCL_DEBUG_FILE="/dev/stderr")
+    env = dict(os.environ, NCCL_DEBUG_FILE="/dev/stderr", RC_P2P_STRICT=strict_flags)
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", os.path.join(ROOT, "tools", "dp_check.py")], capture_output=True, text=True,
                          timeout=600, env=env, cwd=ROOT)
