@@ -24,6 +24,7 @@ fp32): forward, CRPS, backward, gradient all-reduce (N > 1), AdamW.  Prints ONE 
   gpu_eager_baseline — the oracle's modules (plain PyTorch ops, library kernels) run eagerly on the same GPU
   config4 / config5 — whole training step (ms) of one 100k-node graph, 51 members: H=128 fp32 / H=512 bf16 DeepSets
   train_loop_e2e — raincast_gnn_b200.train.run_epoch_engine over a shuffled DataLoader (host collate included), wall clock
+  train_loop_resident — raincast_gnn_b200.train.run_epoch_resident (train.py's default loop: the split lives in HBM), wall clock
   dp_check — data-parallel semantics: the engine's emulated-rank step against the micro-batch oracle (N = 1), replicas
            bit-identical and losses equal to the NCCL exchange (N > 1)
   cpu_baseline — the CPU oracle (reference modules' arithmetic, oracle/) timed on this box's host cores
@@ -55,6 +56,9 @@ WORKLOAD = ("24h_mixed_u reference shape: B=8 graphs/GPU x 122 stations x 11 mem
 MODEL_KW = dict(in_channels=FEATS, hidden_channels_gnn=HIDDEN, out_channels_gnn=HIDDEN, num_layers_gnn=LAYERS,
                 optimizer_class=torch.optim.AdamW, optimizer_params={"lr": 1e-4}, loss="MixedLoss", grad_u="True",
                 u=1.71, xi=0.5)
+
+
+
 
 
 def parse():
@@ -434,6 +438,29 @@ def measure_train_loop(dev, n_dates: int = 512):
             "what": "run_epoch_engine over a shuffled DataLoader: host collate + pin + prefetched H2D + captured step; wall clock"}
 
 
+def measure_train_loop_resident(dev, n_dates: int = 512):
+    """train.py's default epoch loop (run_epoch_resident): the split lives in HBM, the host draws the epoch's order,
+    one gather kernel + one captured step per batch, the ragged last batch stepped eagerly, one loss read per epoch."""
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.pyg_compat import DataLoader
+    from raincast_gnn_b200.train import run_epoch_resident
+    from raincast_gnn_b200.utils.dataset import DeviceSplit, SyntheticEUPPBench
+    ds = SyntheticEUPPBench(n_dates=n_dates + 3, members=MEMBERS)
+    first = next(iter(DataLoader(ds, batch_size=B_PER_GPU)))
+    model = seeded_model(GNN).to(dev).train()
+    eng = TrainEngine(model, first.station_graph, first.x.shape[0], MEMBERS, FEATS, lr=1e-4).capture()
+    split = DeviceSplit([ds[i] for i in range(len(ds))], dev)
+    run_epoch_resident(eng, split, B_PER_GPU)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    loss = run_epoch_resident(eng, split, B_PER_GPU)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"value": len(ds) / dt, "unit": "graphs/s", "epoch_s": dt, "dates": len(ds), "mean_loss": loss,
+            "what": "run_epoch_resident (train.py's default): split resident in HBM, device-side batch gather + captured step; wall clock"}
+
+
 def dp_check(dev, pg, rank, world, steps: int = 4):
     """Data-parallel correctness carried by the bench line (N > 1): after `steps` steps from one initialisation the
     replicas are bit-identical (max |difference| of the flat parameters across ranks = 0), and the peer-memory exchange
@@ -677,7 +704,8 @@ def run_b200(args):
             for key, fn in (("gpu_eager_baseline", lambda: measure_gpu_eager(dev)),
                             ("config4", lambda: dict(measure_scaled_step(dev, HIDDEN, False), workload="one 100k-node graph, 2 978 560 edges, 51 members, H=128, L=4, fp32 (3xTF32 tensor cores)")),
                             ("config5", lambda: dict(measure_scaled_step(dev, 512, True), workload="config-4 graph, bf16 DeepSets (tcgen05 kind::f16), H=512, L=4")),
-                            ("train_loop_e2e", lambda: measure_train_loop(dev))):
+                            ("train_loop_e2e", lambda: measure_train_loop(dev)),
+                            ("train_loop_resident", lambda: measure_train_loop_resident(dev))):
                 try:
                     line[key] = fn()
                 except Exception as exc:            # never lose the bench line over an extra leg

@@ -106,7 +106,6 @@ class TrainEngine:
         self._stage_free = torch.cuda.Event()           # the set being filled is no longer read by a running step
         self._has_staged = False
         self._alt_graph = None                          # graph of the step reading the other input set
-        self._flipped = False                           # the running step reads a set that a prefetch will refill
         self._graph = None
         self.kernels_per_step = None        # librc launches inside one fwd+bwd (counted at capture)
 
@@ -351,7 +350,9 @@ class TrainEngine:
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, pool=self._alt_graph.pool()):
                     self._fwd_bwd()
-            self._flipped = True
+            # the set just left was read by the replay already on this stream: it may be refilled once that has run
+            # (recorded here, not after the coming replay, so that `prefetch` may follow `step` and still overlap it)
+            self._stage_free.record(cur)
             return
         for dst, src in zip((self.x, self.ens, self.y), self._stage):
             dst.copy_(src, non_blocking=True)
@@ -363,9 +364,6 @@ class TrainEngine:
             self.capture()
         if self._graph is not None:
             self._graph.replay()
-            if self._flipped:                         # the other input set may be refilled once this replay has run
-                self._stage_free.record(torch.cuda.current_stream(self.device))
-                self._flipped = False
         else:
             self._fwd_bwd()
         if not self._opt_in_graph:                    # NCCL fallback: all-reduce + AdamW after the captured fwd / bwd

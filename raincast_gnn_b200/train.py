@@ -6,8 +6,9 @@
     python -m raincast_gnn_b200.train --leadtime 24h --dir runs/24h_mixed_u --run_id 0 [--synthetic 64] [--engine]
 
 Additions (all optional): `--synthetic N` trains on N synthetic forecast dates of the reference shape (the
-EUPPBench files need network access), `--engine` replaces the autograd loop by the CUDA-graph engine (same
-arithmetic, no per-step host sync; under torchrun it shards the dates and all-reduces the gradients),
+EUPPBench files need network access), the CUDA-graph engine steps the loop by default (same arithmetic, no
+per-step host sync; under torchrun it shards the dates and exchanges the gradients) with the training split held on
+the GPU (`--host_loader`: per-step host collate + H2D as in the reference; `--autograd`: the reference's loop verbatim),
 `--max_epochs` overrides params.json.
 """
 from __future__ import annotations
@@ -47,8 +48,11 @@ def parse_args(argv=None):
                     help="CUDA-graph training engine: the explicit kernel schedule of one train.py iteration, fused AdamW (default)")
     ap.add_argument("--autograd", dest="engine", action="store_false",
                     help="the reference's loop verbatim: module forward, loss.backward() through torch.autograd, torch.optim.AdamW")
-    ap.add_argument("--resident", action="store_true",
-                    help="with --engine: keep the training split on the GPU and build batches there (no per-step collate / H2D)")
+    ap.add_argument("--resident", dest="resident", action="store_true", default=None,
+                    help="with the engine: keep the training split on the GPU and build batches there (no per-step collate / H2D); "
+                         "the default whenever the split fits in a quarter of the free device memory")
+    ap.add_argument("--host_loader", dest="resident", action="store_false",
+                    help="with the engine: collate every batch on the host and copy it to the GPU, as the reference's DataLoader does")
     return ap.parse_args(argv)
 
 
@@ -128,8 +132,10 @@ def _run_epoch_engine(engine: TrainEngine, loader) -> float:
     return engine.loss_sum.item() / max(done, 1)
 
 
-def run_epoch_resident(engine: TrainEngine, split: DeviceSplit, batch_size: int, generator) -> float:
-    """One pass over a GPU-resident split: a device-side gather builds every batch."""
+def run_epoch_resident(engine: TrainEngine, split: DeviceSplit, batch_size: int, generator=None) -> float:
+    """One pass over a GPU-resident split: a device-side gather builds every batch.  With
+    `generator=None` the epoch's order is drawn from torch's global RNG exactly as `pyg_compat.DataLoader(shuffle=True)`
+    draws it, so this loop and `run_epoch_engine` step through the same batches."""
     engine.loss_sum.zero_()
     batches = split.epoch_batches(batch_size, generator=generator)
     for dates in batches:
@@ -208,20 +214,27 @@ def main(argv=None):
         optimizer = model.optimizer_class(model.parameters(), **model.optimizer_params)
 
     resident = None
-    if args.resident:
-        if engine is None:
-            raise SystemExit("--resident needs --engine")
-        resident = DeviceSplit([fit_part[i] for i in range(len(fit_part))], device)
-        resident_rng = torch.Generator().manual_seed(args.seed + 1000 * rank)
-        LOG.info("training split resident on %s: %.1f MB", device,
-                 (resident.x.numel() + resident.ensemble.numel() + resident.y.numel()) * 4 / 1e6)
+    if args.resident and engine is None:
+        raise SystemExit("--resident needs the engine: drop --autograd")
+    if engine is not None and args.resident is not False:
+        # 180 GB of HBM hold any split of this dataset (3.1k dates x 122 stations x 11 members x 35 features = 0.6 GB):
+        # the batches are then gathered on the device, the host only draws the epoch's order
+        split_bytes = 4 * len(fit_part) * (probe.x.numel() + probe.ensemble.numel() + probe.y.numel())
+        if args.resident or split_bytes < torch.cuda.mem_get_info(device)[0] // 4:
+            try:
+                resident = DeviceSplit([fit_part[i] for i in range(len(fit_part))], device)
+                LOG.info("training split resident on %s: %.1f MB", device, split_bytes / 1e6)
+            except ValueError as exc:                                # graphs of several shapes: no static station graph
+                if args.resident:
+                    raise
+                LOG.info("host loader (%s)", exc)
     os.makedirs(os.path.join(args.dir, "models"), exist_ok=True)
     target = os.path.join(args.dir, "models", f"run_{args.run_id}-best.ckpt")
     best, saved = float("inf"), None
     n_epochs = args.max_epochs or cfg["max_epochs"]
     for epoch in range(1, n_epochs + 1):
         if resident is not None:
-            fit_loss = run_epoch_resident(engine, resident, bs, resident_rng)
+            fit_loss = run_epoch_resident(engine, resident, bs)
         elif engine is not None:
             fit_loss = run_epoch_engine(engine, fit_loader)
         else:

@@ -93,12 +93,20 @@ def test_resident_split_matches_host_batches(run_dir):
 
 
 def test_train_cli_resident(run_dir):
+    """The unchanged command line keeps the training split on the GPU (the engine's default); `--host_loader` collates on
+    the host like the reference's DataLoader.  Both draw the epoch order from torch's global RNG the same way, so the
+    logged losses of the two runs are the same lines."""
+    import re
     from raincast_gnn_b200 import train as rc_train
-    ckpt = rc_train.main(["--leadtime", "24h", "--dir", run_dir, "--run_id", "1", "--synthetic", "40", "--max_epochs", "2", "--engine",
-                          "--resident"])
-    assert os.path.isfile(ckpt)
-    log = open(os.path.join(run_dir, "logs", "train_1.log")).read()
-    assert "resident on" in log and "[Train] Loss:" in log
+    base = ["--leadtime", "24h", "--dir", run_dir, "--synthetic", "43", "--max_epochs", "2"]
+    losses = []
+    for run_id, extra in (("1", []), ("2", ["--host_loader"]), ("3", ["--resident"])):
+        ckpt = rc_train.main(base + ["--run_id", run_id] + extra)
+        assert os.path.isfile(ckpt)
+        log = open(os.path.join(run_dir, "logs", f"train_{run_id}.log")).read()
+        assert ("resident on" in log) == (extra != ["--host_loader"]) and "[Train] Loss:" in log
+        losses.append(re.findall(r"\[Train\] Loss: (\S+)\s+\[Val\] Loss: (\S+)", log))
+    assert len(losses[0]) == 2 and losses[0] == losses[1] == losses[2]
 
 
 def test_epoch_with_ragged_last_batch_matches_reference_loop(run_dir):
