@@ -438,9 +438,10 @@ def measure_train_loop(dev, n_dates: int = 512):
             "what": "run_epoch_engine over a shuffled DataLoader: host collate + pin + prefetched H2D + captured step; wall clock"}
 
 
-def measure_train_loop_resident(dev, n_dates: int = 512):
-    """train.py's default epoch loop (run_epoch_resident): the split lives in HBM, the host draws the epoch's order,
-    one gather kernel + one captured step per batch, the ragged last batch stepped eagerly, one loss read per epoch."""
+def measure_train_loop_resident(dev, n_dates: int = 1024):
+    """train.py's default epoch loop (run_epoch_resident): the split lives in HBM, the host draws the epoch's order and
+    uploads it once, every step is one graph replay (rc_gather_dates_step + the captured step), the ragged last batch is
+    stepped eagerly, one loss read per epoch."""
     from raincast_gnn_b200.engine import TrainEngine
     from raincast_gnn_b200.models import GNN
     from raincast_gnn_b200.pyg_compat import DataLoader
@@ -458,7 +459,8 @@ def measure_train_loop_resident(dev, n_dates: int = 512):
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     return {"value": len(ds) / dt, "unit": "graphs/s", "epoch_s": dt, "dates": len(ds), "mean_loss": loss,
-            "what": "run_epoch_resident (train.py's default): split resident in HBM, device-side batch gather + captured step; wall clock"}
+            "what": "run_epoch_resident (train.py's default): split and the epoch's order resident in HBM, ONE graph replay per step "
+                    "(gather of the next batch + the captured step), ragged last batch stepped eagerly; wall clock"}
 
 
 def dp_check(dev, pg, rank, world, steps: int = 4):

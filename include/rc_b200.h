@@ -338,6 +338,14 @@ int rc_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int rc_gather_dates(const float* x_all, const float* ens_all, const float* y_all, const int64_t* dates, int n_batch,
                     int n_dates, long long x_len, long long ens_len, long long y_len, float* x, float* ens, float* y,
                     int32_t* bad, void* stream);
+/* The same gather for a CAPTURED step (train.py:55-74 as one CUDA graph per batch, nothing written by the host between
+ * replays): `order` (device int64 [n_batches][n_batch]) holds the epoch's shuffled order, the batch taken is number
+ * *step_count - epoch_base[0], where step_count is the optimiser's device-side step counter (rc_adamw_step /
+ * rc_p2p_step advance it), epoch_base[0] its value when the epoch began and epoch_base[1] the number of batches of this
+ * epoch (device int64 [2]).  A batch number outside [0, min(n_batches, epoch_base[1])) sets *bad = 2 and copies nothing. */
+int rc_gather_dates_step(const float* x_all, const float* ens_all, const float* y_all, const int64_t* order, int n_batches,
+                         const int64_t* step_count, const int64_t* epoch_base, int n_batch, int n_dates, long long x_len,
+                         long long ens_len, long long y_len, float* x, float* ens, float* y, int32_t* bad, void* stream);
 
 /* Data-parallel step over NVLink peer memory (the reference, train.py:55-74,185, is single device):
  * every rank keeps its flat gradient where the other ranks of the box can read it, and

@@ -101,6 +101,7 @@ def _declare(lib):
         "rc_head_crps_fwd_bwd": (i, [p, p, p, p, p, p, p, p, p, i, i, i, f, f, f, p]),
         "rc_adamw_step": (i, [p, p, p, p, p, ll, f, f, f, f, f, f, p]),
         "rc_gather_dates": (i, [p, p, p, p, i, i, ll, ll, ll, p, p, p, p, p]),
+        "rc_gather_dates_step": (i, [p, p, p, p, i, p, p, i, i, ll, ll, ll, p, p, p, p, p]),
         "rc_p2p_barrier": (i, [p, p, i, i, i, p, p]),
         "rc_p2p_adamw_step": (i, [p, p, i, p, p, p, ll, f, f, f, f, f, p]),
         "rc_p2p_step": (i, [p, p, p, p, i, i, p, p, p, ll, f, f, f, f, f, p, p]),

@@ -43,12 +43,27 @@ struct GatherDatesP {
   int n_dates;
   float* x; float* ens; float* y;
   int* bad;                            // set to 1 when a date index is out of range (the copy is skipped)
+  // epoch mode (rc_gather_dates_step): `dates` is the epoch's order [n_batches][gridDim.y]; the batch taken is number
+  // *step - base[0] - the optimiser's step counter minus its value at the start of the epoch; base[1] = batches in this
+  // epoch (all on the device: a captured graph takes its next batch with no host write in between); outside
+  // [0, min(n_batches, base[1])): *bad = 2, nothing copied
+  const long long* step; const long long* base;
+  int n_batches;
 };
 
 __global__ void __launch_bounds__(256) gather_dates_kernel(const GatherDatesP p) {
   pdl_entry();
   const int b = blockIdx.y;
-  const long long d = p.dates[b];
+  const long long* dates = p.dates;
+  if (p.step != nullptr) {
+    const long long it = *p.step - p.base[0];
+    if (it < 0 || it >= p.n_batches || it >= p.base[1]) {
+      if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(p.bad, 2);
+      return;
+    }
+    dates += it * gridDim.y;
+  }
+  const long long d = dates[b];
   if (d < 0 || d >= p.n_dates) {
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(p.bad, 1);
     return;
@@ -75,7 +90,24 @@ extern "C" int rc_gather_dates(const float* x_all, const float* ens_all, const f
   const long long total = x_len + ens_len + y_len;
   long long gx = ceil_div_ll(total > 0 ? total : 1, 256);
   if (gx > 2 * kNumSMs) gx = 2 * kNumSMs;
-  const GatherDatesP p{x_all, ens_all, y_all, reinterpret_cast<const long long*>(dates), x_len, ens_len, y_len, n_dates, x, ens, y, bad};
+  const GatherDatesP p{x_all, ens_all, y_all, reinterpret_cast<const long long*>(dates), x_len, ens_len, y_len, n_dates, x, ens, y, bad,
+                       nullptr, nullptr, 0};
+  launch_pdl(gather_dates_kernel, dim3((int)gx, n_batch), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+  return check_launch("gather_dates_kernel");
+}
+
+extern "C" int rc_gather_dates_step(const float* x_all, const float* ens_all, const float* y_all, const int64_t* order, int n_batches,
+                                    const int64_t* step_count, const int64_t* epoch_base, int n_batch, int n_dates, long long x_len,
+                                    long long ens_len, long long y_len, float* x, float* ens, float* y, int32_t* bad, void* stream) {
+  if (!x_all || !ens_all || !y_all || !order || !step_count || !epoch_base || !x || !ens || !y || !bad || n_batches < 0 || n_batch < 0 ||
+      n_dates < 0 || x_len < 0 || ens_len < 0 || y_len < 0)
+    return fail(RC_ERR_ARG, "rc_gather_dates_step: bad argument");
+  if (n_batch == 0) return RC_OK;
+  const long long total = x_len + ens_len + y_len;
+  long long gx = ceil_div_ll(total > 0 ? total : 1, 256);
+  if (gx > 2 * kNumSMs) gx = 2 * kNumSMs;
+  const GatherDatesP p{x_all, ens_all, y_all, reinterpret_cast<const long long*>(order), x_len, ens_len, y_len, n_dates, x, ens, y, bad,
+                       reinterpret_cast<const long long*>(step_count), reinterpret_cast<const long long*>(epoch_base), n_batches};
   launch_pdl(gather_dates_kernel, dim3((int)gx, n_batch), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   return check_launch("gather_dates_kernel");
 }

@@ -296,6 +296,63 @@ class TrainEngine:
                                               self.x.data_ptr(), self.ens.data_ptr(), self.y.data_ptr(), self._bad_date.data_ptr(),
                                               torch.cuda.current_stream(self.device).cuda_stream), "rc_gather_dates")
 
+    def begin_epoch(self, split, batches: torch.Tensor):
+        """Start an epoch over a device-resident split with NO host work per step: `batches` (int64 [n_batches, B], any
+        device) is the epoch's order of full batches.  It goes into a device-side table, the epoch base is pinned to the
+        optimiser's step counter, and every `step_resident()` replays ONE graph = rc_gather_dates_step (batch number
+        step_count - base) + the captured training step.  (train.py:55-62: DataLoader iteration + collate + H2D per step.)"""
+        if self._graph is None:
+            raise _lib.RcError("begin_epoch needs the captured step (TrainEngine.capture())")
+        n, b = int(batches.shape[0]), int(batches.shape[1])
+        stations = split.num_stations
+        if b * stations != self.m or split.x.shape[2] != self.feats or split.ensemble.shape[2] != self.members:
+            raise _lib.RcError(f"begin_epoch: {b} dates of {stations} stations do not make the captured batch of {self.m} nodes")
+        res = getattr(self, "_res", None)
+        if res is None or res["split"] is not split or res["order"].shape[0] < n or res["inputs"] != (self.x.data_ptr(), self.ens.data_ptr()):
+            cap = max(n, (len(split) + b - 1) // b)
+            res = self._res = {"split": split, "order": torch.zeros((cap, b), dtype=torch.int64, device=self.device),
+                               "base": torch.zeros(2, dtype=torch.int64, device=self.device), "graph": None,
+                               "inputs": (self.x.data_ptr(), self.ens.data_ptr())}
+            if getattr(self, "_bad_date", None) is None:
+                self._bad_date = torch.zeros(1, dtype=torch.int32, device=self.device)
+        res["order"][:n].copy_(batches, non_blocking=True)
+        res["base"][:1].copy_(self.step_count.reshape(1))      # [step counter at the start of the epoch, batches in the epoch]
+        res["base"][1:].fill_(n)
+        if res["graph"] is None:
+            self._gather_step()                          # (first launch of this kernel variant outside the capture)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph.pool()):
+                self._gather_step()
+                self._fwd_bwd()
+            res["graph"] = g
+
+    def _gather_step(self):
+        res, split = self._res, self._res["split"]
+        n = split.num_stations
+        _lib.check(_lib.lib().rc_gather_dates_step(split.x.data_ptr(), split.ensemble.data_ptr(), split.y.data_ptr(),
+                                                   res["order"].data_ptr(), res["order"].shape[0], self.step_count.data_ptr(),
+                                                   res["base"].data_ptr(), res["order"].shape[1], len(split), n * self.feats,
+                                                   n * self.members * self.feats, n, self.x.data_ptr(), self.ens.data_ptr(),
+                                                   self.y.data_ptr(), self._bad_date.data_ptr(),
+                                                   torch.cuda.current_stream(self.device).cuda_stream), "rc_gather_dates_step")
+
+    def step_resident(self):
+        """One training step on the next batch of the epoch started by `begin_epoch` (one graph replay)."""
+        self._res["graph"].replay()
+        if not self._opt_in_graph:
+            self._optimizer()
+            self.loss_sum.add_(self.loss)
+        return self.loss
+
+    def check_dates(self):
+        """Raise if a gather saw a date outside the split or a batch number outside the epoch (synchronises the device)."""
+        bad = int(self._bad_date.item()) if getattr(self, "_bad_date", None) is not None else 0
+        if bad:
+            self._bad_date.zero_()
+            raise _lib.RcError("a batch gather read a date index outside the split" if bad == 1 else
+                               "step_resident ran past the batches given to begin_epoch")
+
     def align_ranks(self):
         """A device-side barrier of the ranks on the current stream (peer-memory flags of its own, one tiny kernel, no host
         synchronisation): every rank leaves it within a flag round trip of the last one's arrival.  bench.py calls it

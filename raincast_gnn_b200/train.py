@@ -138,18 +138,22 @@ def run_epoch_resident(engine: TrainEngine, split: DeviceSplit, batch_size: int,
     draws it, so this loop and `run_epoch_engine` step through the same batches."""
     engine.loss_sum.zero_()
     batches = split.epoch_batches(batch_size, generator=generator)
+    full = [d for d in batches if int(d.numel()) * split.num_stations == engine.m]
+    if full:
+        # the epoch's order goes to the device once; every step is then ONE graph replay (gather of the next batch + the
+        # training step): no host work, copy or kernel launch between the steps
+        engine.begin_epoch(split, torch.stack(full))
+        for _ in full:
+            engine.step_resident()
     for dates in batches:
-        if int(dates.numel()) * split.num_stations == engine.m:
-            engine.load_dates(split, dates)
-            engine.step()
-        else:                                              # ragged last batch
-            from .graph import build_station_graph, collate_static
+        if int(dates.numel()) * split.num_stations != engine.m:          # ragged last batch
             b = int(dates.numel())
-            ei, ea = collate_static(split.edge_index, split.edge_attr, split.num_stations, b)
-            g = build_station_graph(ei, ea, b * split.num_stations).to(engine.device)
+            g = split.batched_graph(b)
             engine.step_eager(split.x[dates].reshape(-1, split.x.shape[-1]), split.ensemble[dates].reshape(-1, *split.ensemble.shape[2:]),
                               split.y[dates].reshape(-1), g)
-    return engine.loss_sum.item() / max(len(batches), 1)
+    mean_loss = engine.loss_sum.item() / max(len(batches), 1)
+    engine.check_dates()
+    return mean_loss
 
 
 @torch.no_grad()

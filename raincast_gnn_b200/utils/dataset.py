@@ -94,9 +94,20 @@ class DeviceSplit:
         self.y = torch.stack([g.y.reshape(-1) for g in graphs]).float().contiguous().to(device)
         self.edge_index, self.edge_attr = first.edge_index, first.edge_attr
         self.num_stations = first.x.shape[0]
+        self._graphs = {}
 
     def __len__(self):
         return self.x.shape[0]
+
+    def batched_graph(self, b: int):
+        """The station graph of a batch of `b` dates on the device (PyG collation of the static graph; built once per size -
+        the ragged last batch of every epoch has the same one)."""
+        hit = self._graphs.get(b)
+        if hit is None:
+            from ..graph import build_station_graph, collate_static
+            ei, ea = collate_static(self.edge_index, self.edge_attr, self.num_stations, b)
+            hit = self._graphs[b] = build_station_graph(ei, ea, b * self.num_stations).to(self.x.device)
+        return hit
 
     def epoch_batches(self, batch_size: int, generator=None, shuffle: bool = True):
         """Device int64 index tensors of `batch_size` dates each; like the reference's DataLoader (train.py:155) the last

@@ -553,6 +553,37 @@ def test_gine_tiled_radius_graph(dev, h):
     assert rel_err(_np(de), eps.grad.numpy()) < TOL
 
 
+def test_gine_nan_feature_row(dev):
+    """A NaN node feature.  torch.relu(NaN) is NaN, so PyG hands it to every neighbour's sum; both aggregation paths here
+    compute the message ReLU with an instruction that drops NaN (fmaxf(NaN, 0) = 0 in the warp-per-row kernels,
+    fma.rn.sat in the station-tile kernels): the NaN stays in the row's own self term (1 + eps) x_i and its neighbours
+    get the sum of their other messages.  A documented deviation: node features are standardised inputs /
+    model activations - only the targets y carry NaN, and the CRPS kernel masks those like the reference."""
+    from raincast_gnn_b200 import graph as G, kernels as K
+    from raincast_gnn_b200.utils import synthetic as syn
+    m, h, bad = 20_000, 128, 4321
+    coords = syn.station_coords(m, 450.0, seed=2)
+    ei, ea = G.radius_graph_from_coords(coords, syn.scaled_graph_radius(m, 450.0, 20.0))
+    sg = G.build_station_graph(ei, ea, m).to(dev)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(m, h, generator=g)
+    w, b, eps = torch.randn(h, generator=g), torch.randn(h, generator=g), torch.tensor([0.1])
+    wd, bd, ed = (t.to(dev) for t in (w, b, eps))
+    neighbours = sorted(set(ei[1][ei[0] == bad].tolist()) - {bad})
+    assert len(neighbours) > 5
+    # what the neighbours must get: the aggregation over the graph without the edges that leave `bad`
+    keep = ei[0] != bad
+    sg_cut = G.build_station_graph(ei[:, keep], ea[keep], m).to(dev)
+    want = torch.empty(m, h, device=dev)
+    K.gine_aggr_fwd(x.to(dev), sg_cut, wd, bd, ed, want, tiled=False)
+    x[bad] = float("nan")
+    for tiled in (False, True):
+        out = torch.empty(m, h, device=dev)
+        K.gine_aggr_fwd(x.to(dev), sg, wd, bd, ed, out, tiled=tiled)
+        assert torch.isnan(out).any(dim=1).nonzero().flatten().tolist() == [bad], f"tiled={tiled}"
+        assert rel_err(_np(out[neighbours]), _np(want[neighbours])) < TOL
+
+
 def test_gine_tiled_batched_reference_graphs(dev, golden_graph):
     """160 reference graphs in one batch (19 520 stations): one tile per graph, no halo, bitwise equal results."""
     from oracle import graph as og

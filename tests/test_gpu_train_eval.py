@@ -85,6 +85,24 @@ def test_resident_split_matches_host_batches(run_dir):
             traj.append(float(eng.step().item()))
         trajs.append(traj)
     assert trajs[0] == trajs[1]
+    # the epoch as ONE graph per step (gather of batch number step_count - base + the step): same trajectory again, two
+    # epochs back to back (the second in another order), and a replay past the epoch's batches is reported, not read
+    torch.manual_seed(0)
+    model = GNN(35, cfg["gnn_hidden"], cfg["gnn_hidden"], cfg["gnn_layers"], torch.optim.AdamW, {"lr": 1e-3}, cfg["loss"],
+                cfg["grad_u"], cfg["u"], cfg["xi"]).to(dev).train()
+    eng = TrainEngine(model, first.station_graph, first.x.shape[0], 11, 35, lr=1e-3).capture()
+    eng.begin_epoch(split, torch.stack(order))
+    traj = [float(eng.step_resident().item()) for _ in order]
+    assert traj == trajs[0]
+    eng.begin_epoch(split, torch.stack(order[::-1][:2]))
+    again = [float(eng.step_resident().item()) for _ in range(2)]
+    eng.check_dates()
+    assert again[0] != traj[0] and all(l == l for l in again)
+    eng.begin_epoch(split, torch.stack(order[:1]))
+    eng.step_resident()
+    eng.step_resident()
+    with pytest.raises(_lib.RcError, match="past the batches"):
+        eng.check_dates()
     eng.load_dates(split, torch.tensor([0, 1, 2, 3, 4, 5, 6, 24], device=dev))
     torch.cuda.synchronize()
     assert int(eng._bad_date) == 1
