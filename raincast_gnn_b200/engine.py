@@ -205,16 +205,17 @@ class TrainEngine:
         Ph, Gh = blk["head"]
         if FUSE_HEAD and K.head_crps_blocks(h.shape[0], h.shape[1]) > 0:
             # head Linear + links + CRPS + their backward: one launch instead of three on the chain and one beside it
-            _, d, _ = K.head_crps_fwd_bwd(Ph, h, self.y, self.kind, Gh, u=self.u_fixed, xi=self.xi, t=self.t, loss_out=self.loss)
+            _, d, _ = K.head_crps_fwd_bwd(Ph, h, self.y, self.kind, Gh, u=self.u_fixed, xi=self.xi, t=self.t, loss_out=self.loss,
+                                          flush=False)         # (reduced with the last GINE layer's partials)
         else:
             raw, s_h = K.head_fwd(Ph, h)
             _, d_raw, _ = K.crps_fwd_bwd(raw, self.y, self.kind, raw_input=True, u=self.u_fixed, xi=self.xi, t=self.t,
                                          loss_out=self.loss)
-            d = K.head_bwd(Ph, s_h, d_raw, Gh)
+            d = K.head_bwd(Ph, s_h, d_raw, Gh, flush=False)
         for i in reversed(range(len(blk["layers"]))):
             Pl, Gl = blk["layers"][i]
             d = K.gine_layer_bwd(Pl, saved[i], self.graph, d, Gl, first=(i == 0), training=True)
-        d_emb = K.dimred_bwd(Pr, s_dr, d, Gr)
+        d_emb = K.dimred_bwd(Pr, s_dr, d, Gr, flush=False)        # (reduced with the DeepSets block's partials)
         K.deepsets_bwd(Pd, s_ds, d_emb, Gd)
 
     def _optimizer(self):

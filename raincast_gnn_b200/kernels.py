@@ -42,6 +42,7 @@ class _Side:
     alt = None             # a third stream for the tail of backward (DeepSets / dim_red weight gradients), see on_side(alt=True)
     alt_dirty = False      # work was issued on `alt` that the next reduction / join has to wait for
     keep: list = []
+    pending = None         # the step's GradSink (grad_sink): partials a block left for the next block's flush
 
 
 SIDE = _Side()
@@ -105,6 +106,9 @@ def _wait_alt():
 def join_side():
     if SIDE.stream is None:
         return
+    if SIDE.pending is not None:
+        SIDE.pending.flush()              # (every block sequence of the engine ends on a flushing block: normally empty)
+        SIDE.pending = None
     ev = torch.cuda.Event()
     ev.record(SIDE.stream)
     torch.cuda.current_stream().wait_event(ev)
@@ -207,6 +211,17 @@ class GradSink:
         self.segs, self.keep = [], []
 
 
+def grad_sink(device):
+    """The GradSink of a backward block.  Inside an engine step (side streams set) the blocks share ONE sink, so that a
+    block may leave its partials to the next block's rc_reduce_segments launch (`flush=False`: the head's go with the last
+    GINE layer's, dim_red's with the DeepSets block's) instead of paying a launch of its own."""
+    if SIDE.stream is None:
+        return GradSink(device)
+    if SIDE.pending is None:
+        SIDE.pending = GradSink(device)
+    return SIDE.pending
+
+
 def linear_bwd_weight(dy_op: _lib.rc_operand, x_op: _lib.rc_operand, m, n, k, dw, db, sink: GradSink, *, dw_ld=None,
                       bias_scale=1.0, x2=None, dw2=None):
     """dw[N, k] = dy^T @ x (+ db[N] = bias_scale * column sums of dy).  dy stored [M,N], x stored [M,k].
@@ -253,7 +268,7 @@ def deepsets_bwd(P, saved, d_emb, G, mask_out=None):
     h = P["phi0_w"].shape[0]
     L = _lib.lib()
     dev = ens.device
-    sink = GradSink(dev)
+    sink = grad_sink(dev)
     ho = P["rho2_w"].shape[0]
     # rho[2]
     with on_side(d_emb):
@@ -344,19 +359,20 @@ def dimred_fwd(P, x, emb):
     return y, (x, emb)
 
 
-def dimred_bwd(P, saved, dy, G):
+def dimred_bwd(P, saved, dy, G, *, flush: bool = True):
     x, emb = saved
     m, f = x.shape
     h_in = emb.shape[1]
     w = P["dimred_w"]
     n, ldw = w.shape
-    sink = GradSink(x.device)
+    sink = grad_sink(x.device)
     dw = G["dimred_w"]
     with on_side(dy, alt=True):
         linear_bwd_weight(operand(dy, n), operand(x, f), m, n, f, dw[:, :f], G["dimred_b"], sink, dw_ld=ldw)
     with on_side(dy):
         linear_bwd_weight(operand(dy, n), operand(emb, h_in), m, n, h_in, dw[:, f:], None, sink, dw_ld=ldw)
-        sink.flush()
+        if flush:
+            sink.flush()
     pack = _dimred_pack(P, f)
     if pack is not None:
         pack["ready"] = None                 # one step only: the optimizer changes the weight next
@@ -463,7 +479,7 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     words = bits.shape[1]
     dev = x.device
     st = _stream(x)
-    sink = GradSink(dev)
+    sink = grad_sink(dev)
     do_op = operand(dy, out_dim, RC_OP_BITMASK, bits=bits, ld_bits=words)           # d o = dy * 1[o > 0]
     row_tile = gemm_row_tile(m, hid, out_dim)
     big = u is not None and row_tile == 64          # tensor-core path: the activation GEMMs write their transformed operand out
@@ -495,11 +511,9 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
         gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED, a_out=dt_buf, ld_a_out=hid)
         with on_side(dt_buf):
             linear_bwd_weight(operand(dt_buf, hid), operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
-            sink.flush()
     else:
         with on_side(dz, c0, c1, c2):
             linear_bwd_weight(dt_op, operand(agg, h), m, hid, h, G["nn0_w"], G["nn0_b"], sink)
-            sink.flush()
         gemm(m, h, hid, dt_op, operand(P["nn0_w"], h), d_agg, h, b_layout=RC_B_RED)
     # aggregation backward (+ residual branch of layers > 0)
     dx = _new((m, h), torch.float32, dev)
@@ -513,9 +527,14 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
                                            P["bn_b"].data_ptr(), m, hid, bn_bits.data_ptr(), st), "rc_debug_bn_relu_mask")
         MASKS.active.setdefault("layers", []).append({"msg": msg_bits, "bn": bn_bits, "out": bits})
     part, nb = gine_aggr_bwd(d_agg, x, graph, P["lin_w"], P["lin_b"], P["eps"], None if first else dy, dx)
+    # the per-CTA partials [nb][d w_edge (h) | d b_edge (h) | d eps] join the layer's other split gradients: ONE
+    # rc_reduce_segments launch per layer (float64, fixed order - the arithmetic of rc_gine_aggr_bwd_finalize)
+    flat = part.reshape(-1)
+    sink.add(part, G["lin_w"], 3 * h, nb, h)
+    sink.add(flat[h:], G["lin_b"], 3 * h, nb, h)
+    sink.add(flat[2 * h:], G["eps"], 3 * h, nb, 1)
     with on_side(part, d_agg):
-        _lib.check(L.rc_gine_aggr_bwd_finalize(part.data_ptr(), nb, h, G["lin_w"].data_ptr(), G["lin_b"].data_ptr(),
-                                               G["eps"].data_ptr(), _stream(x)), "rc_gine_aggr_bwd_finalize")
+        sink.flush()
     return dx if need_dx else None
 
 
@@ -524,14 +543,15 @@ def head_fwd(P, x):
     return linear_fwd(x, P["aggr_w"], P["aggr_b"]), (x,)
 
 
-def head_bwd(P, saved, d_raw, G):
+def head_bwd(P, saved, d_raw, G, *, flush: bool = True):
     (x,) = saved
     m, h = x.shape
     c = P["aggr_w"].shape[0]
-    sink = GradSink(x.device)
+    sink = grad_sink(x.device)
     with on_side(d_raw):
         linear_bwd_weight(operand(d_raw, c), operand(x, h), m, c, h, G["aggr_w"], G["aggr_b"], sink)
-        sink.flush()
+        if flush:
+            sink.flush()
     return linear_bwd_data(d_raw, P["aggr_w"])
 
 
@@ -540,7 +560,7 @@ def head_crps_blocks(m: int, hidden: int) -> int:
     return int(_lib.lib().rc_head_crps_blocks(int(m), int(hidden)))
 
 
-def head_crps_fwd_bwd(P, x, y, kind, G, *, u=0.0, xi=0.5, t=5.0, loss_out=None):
+def head_crps_fwd_bwd(P, x, y, kind, G, *, u=0.0, xi=0.5, t=5.0, loss_out=None, flush: bool = True):
     """Head Linear + links + CRPS + backward in ONE launch (small batches): returns (loss float64[1], d_x, n_valid).
     The weight / bias gradient partials are reduced on the side stream."""
     m, h = x.shape
@@ -555,11 +575,14 @@ def head_crps_fwd_bwd(P, x, y, kind, G, *, u=0.0, xi=0.5, t=5.0, loss_out=None):
     _lib.check(_lib.lib().rc_head_crps_fwd_bwd(x.data_ptr(), P["aggr_w"].data_ptr(), P["aggr_b"].data_ptr(), y.data_ptr(), d_x.data_ptr(),
                                                part.data_ptr(), lp.data_ptr(), loss.data_ptr(), n_valid.data_ptr(), m, h, kind,
                                                float(u), float(xi), float(t), _stream(x)), "rc_head_crps_fwd_bwd")
-    sink = GradSink(dev)
+    sink = grad_sink(dev)
     sink.add(part, G["aggr_w"], c * h + c, nb, c * h)
     sink.add(part.reshape(-1)[c * h:], G["aggr_b"], c * h + c, nb, c)
-    with on_side(part, lp):
-        sink.flush()
+    if flush:
+        with on_side(part, lp):
+            sink.flush()
+    else:
+        SIDE.keep.extend((part, lp))
     return loss, d_x, n_valid
 
 
