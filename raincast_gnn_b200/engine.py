@@ -302,8 +302,10 @@ class TrainEngine:
         device) is the epoch's order of full batches.  It goes into a device-side table, the epoch base is pinned to the
         optimiser's step counter, and every `step_resident()` replays ONE graph = rc_gather_dates_step (batch number
         step_count - base) + the captured training step.  (train.py:55-62: DataLoader iteration + collate + H2D per step.)"""
+        if self._graph is None and self.use_cuda_graph:
+            self.capture()
         if self._graph is None:
-            raise _lib.RcError("begin_epoch needs the captured step (TrainEngine.capture())")
+            raise _lib.RcError("begin_epoch needs an engine with CUDA graphs (use load_dates + step otherwise)")
         n, b = int(batches.shape[0]), int(batches.shape[1])
         stations = split.num_stations
         if b * stations != self.m or split.x.shape[2] != self.feats or split.ensemble.shape[2] != self.members:

@@ -3,7 +3,7 @@
 (<dir>/params.json, <dir>/logs/train_<run_id>.log, <dir>/models/run_<run_id>-best.ckpt) and epoch loop
 (train.py:55-91,198-208), driving the B200 kernels.
 
-    python -m raincast_gnn_b200.train --leadtime 24h --dir runs/24h_mixed_u --run_id 0 [--synthetic 64] [--engine]
+    python -m raincast_gnn_b200.train --leadtime 24h --dir runs/24h_mixed_u --run_id 0 [--synthetic 64] [--host_loader | --autograd]
 
 Additions (all optional): `--synthetic N` trains on N synthetic forecast dates of the reference shape (the
 EUPPBench files need network access), the CUDA-graph engine steps the loop by default (same arithmetic, no
@@ -139,12 +139,16 @@ def run_epoch_resident(engine: TrainEngine, split: DeviceSplit, batch_size: int,
     engine.loss_sum.zero_()
     batches = split.epoch_batches(batch_size, generator=generator)
     full = [d for d in batches if int(d.numel()) * split.num_stations == engine.m]
-    if full:
+    if full and engine.use_cuda_graph:
         # the epoch's order goes to the device once; every step is then ONE graph replay (gather of the next batch + the
         # training step): no host work, copy or kernel launch between the steps
         engine.begin_epoch(split, torch.stack(full))
         for _ in full:
             engine.step_resident()
+    else:
+        for dates in full:                                 # (an engine without CUDA graphs: one gather launch per step)
+            engine.load_dates(split, dates)
+            engine.step()
     for dates in batches:
         if int(dates.numel()) * split.num_stations != engine.m:          # ragged last batch
             b = int(dates.numel())

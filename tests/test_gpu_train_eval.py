@@ -23,7 +23,7 @@ def run_dir(tmp_path):
 def test_train_then_eval_cli(run_dir, engine):
     from raincast_gnn_b200 import eval as rc_eval, train as rc_train
     argv = ["--leadtime", "24h", "--dir", run_dir, "--run_id", "0", "--synthetic", "40", "--max_epochs", "2"]
-    ckpt = rc_train.main(argv + (["--engine"] if engine else []))
+    ckpt = rc_train.main(argv + (["--engine"] if engine else ["--autograd"]))
     assert ckpt == os.path.join(run_dir, "models", "run_0-best.ckpt") and os.path.isfile(ckpt)
     log = open(os.path.join(run_dir, "logs", "train_0.log")).read()
     assert "[Train] Loss:" in log and "[Val] Loss:" in log and "[Checkpoint]" in log
