@@ -69,7 +69,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-roofline", action="store_true", help="skip the config-4 aggregation measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch-sweep", action="store_true", help="also report graphs/s at B in {64, 512} per GPU")
+    ap.add_argument("--batch-sweep", action="store_true", help="also report graphs/s at B in {64, 512, 4096} per GPU (SURVEY.md 8d)")
     return ap.parse_args()
 
 
@@ -414,6 +414,50 @@ def measure_scaled_step(dev, hidden: int, bf16: bool, iters: int = 3):
     return out
 
 
+def measure_batch_sweep(dev, batches=(64, 512, 4096)):
+    """The reference-shape training step at larger per-GPU batches (SURVEY.md 8d's sweep): the same model and station
+    graph, B dates collated into one batch.  B = 8 is launch / dependency latency; from a few hundred graphs on the step
+    is throughput bound (M >= 16k rows: tensor-core Linears, tiled aggregation).  L2 flushed between steps up to
+    B = 512 (the B = 4096 inputs alone are 7x L2)."""
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.graph import build_station_graph
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.utils import synthetic as syn
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for b in batches:
+        _, _, ei_b, ea_b = static_graph(b)
+        m = b * N_STATIONS
+        sg = build_station_graph(ei_b, ea_b, m).to(dev)
+        model = seeded_model(GNN).to(dev).train()
+        graph = m < 16384                       # large steps are not launch bound: kernels issued eagerly
+        eng = TrainEngine(model, sg, m, MEMBERS, FEATS, lr=1e-4, use_cuda_graph=graph)
+        if graph:
+            eng.capture()
+        x, ens = syn.node_features(m, MEMBERS, FEATS, seed=11)
+        y = syn.log_precip_targets(m, seed=11)
+        eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
+        iters = 20 if b <= 512 else 5
+        for _ in range(3):
+            eng.step()
+        total = 0.0
+        for _ in range(iters):
+            if b <= 512:
+                flush.zero_()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.step()
+            c.record()
+            c.synchronize()
+            total += a.elapsed_time(c)
+        ms = total / iters
+        out[str(b)] = {"ms_per_step": ms, "graphs_per_s": b / (ms * 1e-3), "nodes": m, "edges": int(ei_b.shape[1]),
+                       "cuda_graph": graph, "loss": float(eng.loss.item())}
+        del eng, model, sg, x, ens, y
+        torch.cuda.empty_cache()
+    return out
+
+
 def measure_train_loop(dev, n_dates: int = 512):
     """train.py's epoch loop as shipped (run_epoch_engine): DataLoader collate on the host, pinning, the next batch's
     H2D copy prefetched on a copy stream, one captured step per batch, the ragged last batch stepped eagerly, one loss
@@ -686,6 +730,7 @@ def run_b200(args):
                     tr = json.load(f)
                 line["roofline"]["traffic"] = tr.get("gine_aggr_fwd_dram_bytes")
                 line["roofline"]["bwd"]["traffic"] = tr.get("gine_aggr_bwd_dram_bytes")
+                line["roofline"]["traffic_source"] = "profiles/traffic.json (one ncu --set full capture of the same kernels; not re-measured by this run)"
             except OSError:
                 pass
         if not args.no_roofline:
@@ -712,6 +757,11 @@ def run_b200(args):
                     line[key] = fn()
                 except Exception as exc:            # never lose the bench line over an extra leg
                     line[key] = {"error": repr(exc)}
+        if world == 1 and args.batch_sweep:
+            try:
+                line["batch_sweep"] = measure_batch_sweep(dev)
+            except Exception as exc:
+                line["batch_sweep"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             sps, done, dt, cores = cpu_steps_per_second(10_000, 3, budget_s=12.0)
             line["cpu_baseline"] = {"value": sps * B_PER_GPU, "unit": "graphs/s", "cores": cores, "kind": "port",

@@ -1,5 +1,7 @@
 """Experiment: GINE aggregation, warp-per-row vs station-tile kernels, on the config-4 graph and on a large batch of
-reference graphs.  L2 flushed between launches; CUDA events.  usage: exp_tiled.py [iters] [which: c4,ref,all]"""
+reference graphs.  L2 flushed between launches; CUDA events.  usage: exp_tiled.py [iters] [which: c4,c4x10,ref,all]
+c4x10: SURVEY.md 8d's optional x10 graph (1 M nodes, same mean degree): x = 512 MB, four times L2, so the gathered rows
+come from HBM whatever the flush does."""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -51,6 +53,10 @@ if which in ("c4", "all"):
     n = 100_000
     ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
     run("config 4", ei, ea, n)
+if which == "c4x10":
+    n = 1_000_000
+    ei, ea = G.radius_graph_from_coords(syn.station_coords(n, 1000.0, 0), syn.scaled_graph_radius(n, 1000.0))
+    run("config 4 x 10", ei, ea, n)
 if which in ("ref", "all"):
     coords = syn.station_coords(122, 600.0, 0)
     ei1, ea1 = G.radius_graph(syn.distance_matrix(coords), 100.0)
