@@ -414,48 +414,57 @@ def measure_scaled_step(dev, hidden: int, bf16: bool, iters: int = 3):
     return out
 
 
+def measure_refshape_step(dev, b: int, hidden: int = HIDDEN, bf16: bool = False, flush=None):
+    """The training step on `b` collated reference station graphs: ms per step (CUDA events per step, L2 flushed between
+    steps when `flush` is given).  One CUDA graph while the step is launch bound (M < 16k rows), eager beyond."""
+    from raincast_gnn_b200.engine import TrainEngine
+    from raincast_gnn_b200.graph import build_station_graph
+    from raincast_gnn_b200.models import GNN
+    from raincast_gnn_b200.utils import synthetic as syn
+    _, _, ei_b, ea_b = static_graph(b)
+    m = b * N_STATIONS
+    sg = build_station_graph(ei_b, ea_b, m).to(dev)
+    kw = dict(MODEL_KW, hidden_channels_gnn=hidden, out_channels_gnn=hidden)
+    model = GNN(**kw)
+    model.load_state_dict(syn.seeded_state_dict(model.state_dict(), seed=2024))
+    model.to(dev).train()
+    if bf16:
+        model.deepset.compute_dtype = "bf16"
+    graph = m < 16384
+    eng = TrainEngine(model, sg, m, MEMBERS, FEATS, lr=1e-4, use_cuda_graph=graph)
+    if graph:
+        eng.capture()
+    x, ens = syn.node_features(m, MEMBERS, FEATS, seed=11)
+    y = syn.log_precip_targets(m, seed=11)
+    eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
+    iters = 20 if b <= 512 else 5
+    for _ in range(3):
+        eng.step()
+    total = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.step()
+        c.record()
+        c.synchronize()
+        total += a.elapsed_time(c)
+    ms = total / iters
+    out = {"ms_per_step": ms, "graphs_per_s": b / (ms * 1e-3), "nodes": m, "edges": int(ei_b.shape[1]),
+           "cuda_graph": graph, "launches_per_step": eng.launches_per_step, "loss": float(eng.loss.item())}
+    del eng, model, sg, x, ens, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_batch_sweep(dev, batches=(64, 512, 4096)):
     """The reference-shape training step at larger per-GPU batches (SURVEY.md 8d's sweep): the same model and station
     graph, B dates collated into one batch.  B = 8 is launch / dependency latency; from a few hundred graphs on the step
     is throughput bound (M >= 16k rows: tensor-core Linears, tiled aggregation).  L2 flushed between steps up to
     B = 512 (the B = 4096 inputs alone are 7x L2)."""
-    from raincast_gnn_b200.engine import TrainEngine
-    from raincast_gnn_b200.graph import build_station_graph
-    from raincast_gnn_b200.models import GNN
-    from raincast_gnn_b200.utils import synthetic as syn
-    out = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for b in batches:
-        _, _, ei_b, ea_b = static_graph(b)
-        m = b * N_STATIONS
-        sg = build_station_graph(ei_b, ea_b, m).to(dev)
-        model = seeded_model(GNN).to(dev).train()
-        graph = m < 16384                       # large steps are not launch bound: kernels issued eagerly
-        eng = TrainEngine(model, sg, m, MEMBERS, FEATS, lr=1e-4, use_cuda_graph=graph)
-        if graph:
-            eng.capture()
-        x, ens = syn.node_features(m, MEMBERS, FEATS, seed=11)
-        y = syn.log_precip_targets(m, seed=11)
-        eng.load_batch(x.to(dev), ens.to(dev), y.to(dev))
-        iters = 20 if b <= 512 else 5
-        for _ in range(3):
-            eng.step()
-        total = 0.0
-        for _ in range(iters):
-            if b <= 512:
-                flush.zero_()
-            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            eng.step()
-            c.record()
-            c.synchronize()
-            total += a.elapsed_time(c)
-        ms = total / iters
-        out[str(b)] = {"ms_per_step": ms, "graphs_per_s": b / (ms * 1e-3), "nodes": m, "edges": int(ei_b.shape[1]),
-                       "cuda_graph": graph, "loss": float(eng.loss.item())}
-        del eng, model, sg, x, ens, y
-        torch.cuda.empty_cache()
-    return out
+    return {str(b): measure_refshape_step(dev, b, flush=flush if b <= 512 else None) for b in batches}
 
 
 def measure_train_loop(dev, n_dates: int = 512):
@@ -751,6 +760,7 @@ def run_b200(args):
             for key, fn in (("gpu_eager_baseline", lambda: measure_gpu_eager(dev)),
                             ("config4", lambda: dict(measure_scaled_step(dev, HIDDEN, False), workload="one 100k-node graph, 2 978 560 edges, 51 members, H=128, L=4, fp32 (3xTF32 tensor cores)")),
                             ("config5", lambda: dict(measure_scaled_step(dev, 512, True), workload="config-4 graph, bf16 DeepSets (tcgen05 kind::f16), H=512, L=4")),
+                            ("config5_reference_shape", lambda: dict(measure_refshape_step(dev, B_PER_GPU, 512, True, flush), workload="B=8 reference graphs x 11 members, bf16 DeepSets (tcgen05 kind::f16), H=512, L=4; one CUDA graph, L2 flushed between steps")),
                             ("train_loop_e2e", lambda: measure_train_loop(dev)),
                             ("train_loop_resident", lambda: measure_train_loop_resident(dev))):
                 try:
