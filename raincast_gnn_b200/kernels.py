@@ -141,6 +141,15 @@ def gemm(m, n, k, a: _lib.rc_operand, b: _lib.rc_operand, d, ldd, *, a_layout=RC
     return g
 
 
+def gemm_on_tensor_cores(m, n, k) -> bool:
+    """True when gemm() runs an m x n activation GEMM over k on the tcgen05 kernels (rc_gemm_tc_workspace > 0).  Only that
+    path writes `a_out` for the BatchNorm / bit-mask / affine prologues; the SIMT kernels write it for RC_OP_GINE_AGGR only."""
+    g = _lib.rc_gemm()
+    g.m, g.n, g.k, g.splits = m, n, k, 1
+    g.a_layout, g.b_layout = RC_A_ROW, RC_B_COL
+    return bool(k) and int(_lib.lib().rc_gemm_tc_workspace(C.byref(g))) > 0
+
+
 def gemm_row_tile(m, n, k=0) -> int:
     """Rows per statistics tile of the forward GEMM gemm() would launch for an m x n output over k."""
     g = _lib.rc_gemm()
@@ -463,7 +472,9 @@ def gine_layer_fwd(P, x, graph, *, first: bool, training: bool):
     bits = _new((m, words), torch.int32, dev)
     # large graphs (tensor-core Linear layers): u = relu(BN(t)) is written out by the GEMM's operand producer and the
     # backward's weight-gradient GEMM reads it back instead of recomputing it element by element
-    u = _new((m, hid), torch.float32, dev) if (training and SAVE_OPERANDS and gemm_row_tile(m, out_dim, hid) == 64) else None
+    # (asked of the library, not inferred from the row tile: a SIMT GEMM with 64-row tiles - 9.4k to 16k rows at H=128,
+    # from 2.3k rows at H=512 - does not write u)
+    u = _new((m, hid), torch.float32, dev) if (training and SAVE_OPERANDS and gemm_on_tensor_cores(m, out_dim, hid)) else None
     gemm(m, out_dim, hid, operand(t, hid, RC_OP_BN_RELU, (mean, rstd, P["bn_w"], P["bn_b"])), operand(P["nn3_w"], hid),
          y, out_dim, bias=P["nn3_b"], epi=RC_EPI_RELU if first else RC_EPI_RELU_RES, res=None if first else x,
          ld_res=h, bits_out=bits, ld_bits_out=words, a_out=u, ld_a_out=hid)
@@ -482,7 +493,8 @@ def gine_layer_bwd(P, saved, graph, dy, G, *, first: bool, training: bool = True
     sink = grad_sink(dev)
     do_op = operand(dy, out_dim, RC_OP_BITMASK, bits=bits, ld_bits=words)           # d o = dy * 1[o > 0]
     row_tile = gemm_row_tile(m, hid, out_dim)
-    big = u is not None and row_tile == 64          # tensor-core path: the activation GEMMs write their transformed operand out
+    # tensor-core path: the activation GEMMs write their transformed operand out
+    big = u is not None and gemm_on_tensor_cores(m, hid, out_dim) and gemm_on_tensor_cores(m, h, hid)
     # Linear2: d W2 = d o^T u,  u = relu(BN(t)) recomputed in the prologue (small graphs) or saved by the forward (large)
     if not big:
         with on_side(dy):

@@ -81,9 +81,24 @@ def _case(members, dev, n_dates=8, hidden=128, layers=4, **ds_kw):
 @pytest.mark.parametrize("members", [11, 51])
 def test_reference_shape_mask_matched_gradients(dev, members):
     """BASELINE.json config 2 shape: B=8 x 122 stations x 11 / 51 members, H=128, L=4, mixed_u - every gradient at 1e-5."""
-    from oracle import masked
     torch.set_num_threads(8)
     batch, model, sd, kw = _case(members, dev)
+    _check_mask_matched(batch, model, sd, kw, dev)
+
+
+@pytest.mark.parametrize("n_dates,hidden", [(64, 128), (128, 128), (24, 512)])
+def test_mid_size_batches_mask_matched_gradients(dev, n_dates, hidden):
+    """Batches between the reference shape and the tensor-core regime (16 384 rows): the SIMT Linear layers pick 32-row
+    tiles at B=64 / H=128 and 64-row tiles at B=128 / H=128 (15 616 rows) and at B=24 / H=512.  64 rows is also the
+    statistics tile of the tensor-core kernels, which - unlike the SIMT ones - write the transformed operands out for
+    the weight-gradient GEMMs; the layer must ask the library which path runs, not infer it from the tile."""
+    torch.set_num_threads(8)
+    batch, model, sd, kw = _case(11, dev, n_dates=n_dates, hidden=hidden)
+    _check_mask_matched(batch, model, sd, kw, dev)
+
+
+def _check_mask_matched(batch, model, sd, kw, dev):
+    from oracle import masked
     preds, loss, grads, masks = cuda_step_with_masks(model, batch, dev)
     args = dict(num_layers=kw["num_layers_gnn"], loss=kw["loss"], grad_u=kw["grad_u"], u=kw["u"], xi=kw["xi"])
     cpu_masks = {k: v.cpu() for k, v in masks.items()}
