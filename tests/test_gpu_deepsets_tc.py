@@ -29,7 +29,8 @@ def _unpack(bits, h):
 
 
 @pytest.mark.parametrize("m,em,f,h,bf16", [(7001, 11, 35, 128, 0), (1400, 51, 35, 128, 0), (6500, 11, 35, 256, 0), (1300, 51, 33, 128, 0),
-                                           (1400, 51, 35, 512, 1), (6100, 11, 40, 128, 0)])
+                                           (1400, 51, 35, 512, 1), (6100, 11, 40, 128, 0),
+                                           (6500, 11, 35, 64, 0), (6500, 11, 35, 96, 0), (1300, 51, 35, 192, 0)])   # widths that are not multiples of 128
 def test_pool_bwd_tensor_cores_mask_matched(dev, m, em, f, h, bf16):
     from raincast_gnn_b200 import _lib
     L = _lib.lib()

@@ -86,10 +86,12 @@ def test_reference_shape_mask_matched_gradients(dev, members):
     _check_mask_matched(batch, model, sd, kw, dev)
 
 
-@pytest.mark.parametrize("n_dates,hidden", [(64, 128), (128, 128), (24, 512)])
+@pytest.mark.parametrize("n_dates,hidden", [(64, 128), (128, 128), (24, 512), (40, 256), (16, 64), (135, 128)])
 def test_mid_size_batches_mask_matched_gradients(dev, n_dates, hidden):
     """Batches between the reference shape and the tensor-core regime (16 384 rows): the SIMT Linear layers pick 32-row
-    tiles at B=64 / H=128 and 64-row tiles at B=128 / H=128 (15 616 rows) and at B=24 / H=512.  64 rows is also the
+    tiles at B=64 / H=128 and 64-row tiles at B=128 / H=128 (15 616 rows), B=24 / H=512 and B=40 / H=256; H=64 is narrower
+    than a column tile and off the fused head + CRPS kernel; B=135 (16 470 rows) is the first batch on the tensor-core Linears
+    and the station-tile aggregation (one tile per graph, empty halo).  64 rows is also the
     statistics tile of the tensor-core kernels, which - unlike the SIMT ones - write the transformed operands out for
     the weight-gradient GEMMs; the layer must ask the library which path runs, not infer it from the tile."""
     torch.set_num_threads(8)
