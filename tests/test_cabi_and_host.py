@@ -356,3 +356,16 @@ def test_euppbench_reads_reference_processed_file_without_pyg(tmp_path):
         EUPPBench(str(tmp_path), str(tmp_path), "24h", 100.0, split="nope")              # utils/dataset.py:52-53
     with pytest.raises(FileNotFoundError):
         EUPPBench(str(tmp_path), str(tmp_path), "72h", 100.0, split="train_rf")
+
+
+@pytest.mark.parametrize("m,h,row_tile", [(976, 128, 8), (7808, 128, 32), (15616, 128, 64), (2928, 512, 64), (4880, 256, 64)])
+def test_row_tile_does_not_identify_the_tensor_core_path(m, h, row_tile):
+    """rc_gemm_row_tile / rc_gemm_tc_workspace are host-side answers (no device needed).  Below 16 384 rows the SIMT
+    Linear also picks 64-row tiles once they fill the SMs, the statistics tile of the tensor-core kernels; only
+    rc_gemm_tc_workspace > 0 says that the tensor-core kernels - the ones that write rc_gemm.a_out for every operand
+    prologue - will run (kernels.gine_layer_fwd / _bwd choose their weight-gradient operands by it)."""
+    from raincast_gnn_b200 import kernels as K
+    assert K.gemm_row_tile(m, h, h) == row_tile
+    assert not K.gemm_on_tensor_cores(m, h, h)
+    if os.environ.get("RC_GEMM_TC", "1") != "0":
+        assert K.gemm_on_tensor_cores(16384, h, h) and K.gemm_row_tile(16384, h, h) == 64
