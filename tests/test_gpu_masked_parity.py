@@ -132,6 +132,30 @@ def test_engine_step_matches_module_path_between_the_shapes(dev, n_dates, hidden
             assert rel_err(c.cpu().numpy(), a.cpu().numpy()) < TOL, k
 
 
+@pytest.mark.parametrize("n_dates,hidden", [(128, 128), (135, 128), (24, 512)])
+def test_eval_mode_forward_between_the_shapes(dev, n_dates, hidden):
+    """eval.py's forward (BatchNorm on running statistics, no gradient) on mid-size batches - SIMT 64-row tiles, the first
+    tensor-core batch, H=512 - and on eval.py's member sub-graphs (utils/data.py:418-431: 10 members) against the float64
+    oracle in eval mode: predictions at 1e-5."""
+    from oracle import model as om, pyg as opyg
+    torch.set_num_threads(8)
+    batch, model, sd, kw = _case(11, dev, n_dates=n_dates, hidden=hidden)
+    ref = om.GNN(**kw)
+    ref.load_state_dict(sd)
+    ref = ref.double().eval()
+    ref.conv.force_float = False
+    model.eval()
+    for members in (11, 10):
+        ens = batch.ensemble[:, :members].contiguous()
+        with torch.no_grad():
+            want = ref(opyg.Data(x=batch.x.double(), ensemble=ens.double(), edge_index=batch.edge_index,
+                                 edge_attr=batch.edge_attr.double()))
+            b = batch.to(dev)
+            b.ensemble = ens.to(dev)
+            got = model(b)
+        assert rel_err(got.cpu().numpy(), want.numpy()) < TOL, members
+
+
 def _check_mask_matched(batch, model, sd, kw, dev):
     from oracle import masked
     preds, loss, grads, masks = cuda_step_with_masks(model, batch, dev)
