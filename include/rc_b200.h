@@ -219,7 +219,8 @@ typedef struct rc_gemm {
   void* tc_ws; size_t tc_ws_bytes;
   float* a_out; int ld_a_out;   /* the A operand after its prologue, written once (nullable): RC_OP_GINE_AGGR on the SIMT
                                    path, every prologue on the tensor-core activation path (the layer's weight-gradient
-                                   GEMM then takes it as a plain operand) */
+                                   GEMM then takes it as a plain operand).  Which path runs is rc_gemm_tc_workspace(g) > 0 -
+                                   NOT the row tile: the SIMT kernels also pick 64-row tiles once those fill the SMs */
   int b_static;                 /* 1: the B operand is a parameter and res / e_aux are saved activations - the kernel
                                    launched just before this one on the stream writes none of them.  The kernel then fetches its first B tile BEFORE waiting for that
                                    kernel (programmatic dependent launch), overlapping the fetch with its tail */
